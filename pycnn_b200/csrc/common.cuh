@@ -1,0 +1,243 @@
+// common.cuh -- context, error plumbing and launch helpers for libpycnn_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pycnn_b200.h"
+
+namespace pb {
+
+// ---------------------------------------------------------------------------------------------
+// errors: thread-local message, int return codes, nothing throws across the ABI
+// ---------------------------------------------------------------------------------------------
+inline thread_local char g_err[1024] = "";
+
+inline int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define PB_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return pb::fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define PB_CHECK(cond, ...)                  \
+  do {                                       \
+    if (!(cond)) return pb::fail(__VA_ARGS__); \
+  } while (0)
+
+#define PB_TRY(expr)          \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// ---------------------------------------------------------------------------------------------
+// kernel classes for per-class event timing (pycnn_b200_kernel_stats)
+// ---------------------------------------------------------------------------------------------
+enum KernelClass : int {
+  KC_EXTRACT = 0,   // fused conv3x3 + ReLU + 2x2 max-pool + flatten
+  KC_GATHER,        // batch row gather
+  KC_GEMM_FWD,      // forward GEMMs (bias/ReLU epilogue)
+  KC_GEMM_DA,       // backward dA GEMMs (ReLU-mask epilogue)
+  KC_GEMM_DW,       // backward dW GEMMs
+  KC_SOFTMAX_CE,    // softmax + CE + argmax + dZ
+  KC_COLSUM,        // bias gradients
+  KC_SQNORM,        // per-tensor gradient norms
+  KC_UPDATE,        // clipped SGD / Adam
+  KC_ALLREDUCE,     // NCCL gradient all-reduce (time on the compute stream)
+  KC_MISC,          // converts, memsets, epilogue fix-ups
+  KC_COUNT
+};
+
+static const char* const kKernelClassNames[KC_COUNT] = {
+    "extract_conv_relu_pool", "gather_rows", "gemm_forward", "gemm_dA", "gemm_dW", "softmax_ce_grad",
+    "bias_colsum", "grad_sqnorm", "clip_update", "allreduce", "misc"};
+
+struct TimedLaunch {
+  cudaEvent_t a, b;
+};
+
+// flat parameter layout entry
+struct TensorDesc {
+  int64_t off;   // offset in floats into the flat buffers
+  int64_t rows;  // out
+  int64_t cols;  // in (1 for biases: stored as a single row of `rows` values -> rows=1, cols=out)
+  int64_t ld;    // row pitch in floats (multiple of 4)
+};
+
+struct Chunk {  // unit of work for sqnorm/update kernels
+  int tensor;
+  int pad;
+  int64_t off;
+  int64_t len;
+};
+
+struct NcclApi;  // comm.cuh
+
+}  // namespace pb
+
+// The opaque context (global namespace: it is the C ABI's handle type).
+struct pycnn_b200_ctx {
+  int device = 0;
+  int num_sms = 148;
+  size_t l2_bytes = 0;
+  cudaStream_t stream = nullptr;       // compute
+  cudaStream_t copy_stream = nullptr;  // H2D staging for streamed batches
+  cudaEvent_t events[16] = {};
+  cudaEvent_t copy_done = nullptr, compute_done = nullptr;
+  int math_mode = PYCNN_B200_MATH_TF32;
+  int update_rule = PYCNN_B200_RULE_CPU;
+  int extract_mode = PYCNN_B200_EXTRACT_TC;
+
+  // filters
+  int F = 0;
+  std::vector<double> h_taps;   // as given by the user [F][3][3]
+  float* d_taps = nullptr;      // flipped, [F][9] fp32 (SIMT path)
+  void* d_tc_filters = nullptr; // packed B operand for the tensor-core extractor
+  int tc_ncols = 0;             // accumulator columns used by the TC extractor
+  float* d_tc_scale = nullptr;  // per-filter epilogue scale for the TC extractor
+
+  // network
+  int64_t D = 0, Dp = 0;
+  int L = 0, C = 0;
+  std::vector<int64_t> dims;            // [D, n1..nL, C]
+  std::vector<int64_t> ldw;             // pitch of act/feature rows per level: pad4(dims[i])
+  std::vector<pb::TensorDesc> tensors;  // 2*(L+1): w,b per layer
+  int64_t P = 0;                        // flat length in floats
+  float *d_params = nullptr, *d_grads = nullptr, *d_m = nullptr, *d_v = nullptr;
+  pb::Chunk* d_chunks = nullptr;
+  int num_chunks = 0;
+  double* d_norm2 = nullptr;
+
+  // optimizer
+  int opt = PYCNN_B200_OPT_SGD;
+  double lr = 1e-3, beta1 = 0.9, beta2 = 0.999, eps = 1e-8;
+  int64_t t = 0;
+
+  // dataset
+  int64_t cap_rows = 0, n_rows = 0;
+  float* d_feat = nullptr;
+  int32_t* d_labels = nullptr;
+
+  // batch workspace
+  int64_t bs_cap = 0;
+  int64_t* d_idx = nullptr;
+  int64_t idx_cap = 0;
+  int32_t* d_blabels = nullptr;
+  float* d_x = nullptr;               // gathered batch [bs, Dp]
+  std::vector<float*> d_act;          // [L] hidden activations [bs, ldw[l+1]]
+  std::vector<float*> d_dz;           // [L+1] dZ per layer [bs, ldw[l+1]]
+  float* d_probs = nullptr;           // [bs, ldw[L+1]]
+  int32_t* d_pred = nullptr;          // [bs]
+  float* d_conf = nullptr;            // [bs]
+  float* d_gemm_ws = nullptr;         // split-K workspace
+  size_t gemm_ws_bytes = 0;
+
+  // stats accumulators: [0] loss (double), [1] correct (as unsigned long long bits)
+  double* d_stats = nullptr;
+  double* h_stats = nullptr;  // pinned
+
+  // staging
+  uint8_t* d_images = nullptr;
+  size_t images_cap = 0;
+  int32_t* d_img_labels = nullptr;
+  size_t img_labels_cap = 0;
+  void* d_scratch = nullptr;  // generic device scratch (f64 staging for host<->device converts)
+  size_t scratch_cap = 0;
+  void* h_pinned = nullptr;   // pinned bounce buffer
+  size_t pinned_cap = 0;
+  float* d_flush = nullptr;   // L2 flush buffer
+  size_t flush_bytes = 0;
+
+  // comm
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+
+  // timing
+  bool timing = false;
+  std::vector<pb::TimedLaunch> timed[pb::KC_COUNT];
+  std::vector<cudaEvent_t> event_pool;
+  int64_t class_launches[pb::KC_COUNT] = {};
+  double class_ms[pb::KC_COUNT] = {};
+  int64_t launches = 0;
+
+  // TMA descriptor encoder (driver entry point resolved at create time)
+  void* encode_tiled = nullptr;
+};
+
+namespace pb {
+
+// RAII-ish scope that brackets one launch with events when timing is on.
+struct LaunchScope {
+  pycnn_b200_ctx* c;
+  int cls;
+  cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(pycnn_b200_ctx* ctx, int k, int n_launches = 1) : c(ctx), cls(k) {
+    c->launches += n_launches;
+    c->class_launches[cls] += n_launches;
+    if (c->timing) {
+      a = take();
+      b = take();
+      cudaEventRecord(a, c->stream);
+    }
+  }
+  ~LaunchScope() {
+    if (c->timing) {
+      cudaEventRecord(b, c->stream);
+      c->timed[cls].push_back({a, b});
+    }
+  }
+  cudaEvent_t take() {
+    cudaEvent_t e;
+    if (!c->event_pool.empty()) {
+      e = c->event_pool.back();
+      c->event_pool.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
+  }
+};
+
+static inline int ensure_scratch(pycnn_b200_ctx* c, size_t bytes) {
+  if (bytes <= c->scratch_cap) return 0;
+  if (c->d_scratch) PB_CUDA(cudaFree(c->d_scratch));
+  c->d_scratch = nullptr;
+  c->scratch_cap = 0;
+  size_t cap = (size_t)round_up((int64_t)bytes, 1 << 20);
+  PB_CUDA(cudaMalloc(&c->d_scratch, cap));
+  c->scratch_cap = cap;
+  return 0;
+}
+
+static inline int ensure_pinned(pycnn_b200_ctx* c, size_t bytes) {
+  if (bytes <= c->pinned_cap) return 0;
+  if (c->h_pinned) PB_CUDA(cudaFreeHost(c->h_pinned));
+  c->h_pinned = nullptr;
+  c->pinned_cap = 0;
+  size_t cap = (size_t)round_up((int64_t)bytes, 1 << 20);
+  PB_CUDA(cudaMallocHost(&c->h_pinned, cap));
+  c->pinned_cap = cap;
+  return 0;
+}
+
+}  // namespace pb

@@ -1,0 +1,326 @@
+// gemm_tc.cuh -- the dense-MLP GEMMs on 5th-gen tensor cores (K2 of SURVEY 2.3).
+//
+//   C[M,N] (+)= A . B     TF32 operands, FP32 accumulation in TMEM, tcgen05.mma cta_group::1
+//
+// Three operand-layout forms cover forward, dA and dW with row-major storage everywhere
+// (forward_pass.pyx:29,36 / backward_pass.pyx:71,75,92,97):
+//   forward  Z  = X . W^T   A = X  [M=bs , K=in ] K-major     B = W  [N=out, K=in ] K-major
+//   dA       dA = dZ . W    A = dZ [M=bs , K=out] K-major     B = W  [K=out, N=in ] MN-major
+//   dW       dW = dZ^T . X  A = dZ [K=bs , M=out] MN-major    B = X  [K=bs , N=in ] MN-major
+//
+// Pipeline (one 128 x BN output tile per CTA, optional split-K over gridDim.z):
+//   warp 0 (1 thread)  TMA producer: cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier expect_tx
+//   warp 1 (1 thread)  MMA issuer: 4 x tcgen05.mma (K=8 each) per 32-wide k-block, tcgen05.commit
+//                      releases the smem stage / signals the epilogue
+//   warps 2-5          epilogue: tcgen05.ld (32 lanes x 32 cols) -> bias / ReLU / ReLU-mask ->
+//                      128-bit global stores, or red.global.add.v4.f32 for split-K partials
+// K-major tiles are [rows][32 floats] with SWIZZLE_128B (SBO 1024 B); MN-major tiles are
+// [MN/32 atoms][32 k-rows][32 floats] (LBO = 4096 B between atoms, SBO = 1024 B between 8-row
+// groups), loaded by ONE 3-D TMA box per operand (dims {32, K, MN/32}, strides {pitch, 128 B}).
+#pragma once
+#include "elementwise.cuh"
+#include "tc_common.cuh"
+
+namespace pb {
+namespace tc {
+
+constexpr int G_BM = 128;
+constexpr int G_BK = 32;  // floats: one 128-byte swizzle row
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = G_BM * G_BK * 4;       // 16 KB
+  static constexpr int B_BYTES = BN * G_BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int MAX_STAGES = (224 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TcGemmArgs {
+  float* C;
+  int64_t ldc;
+  int M, N, K;
+  int epi;      // 0 none, 1 +bias, 2 relu(+bias), 3 mask (only when !atomic)
+  int atomic;   // 1: accumulate partial sums with red.add (split-K); epilogue applied by gemm_fixup_kernel
+  int num_kb;        // total 32-wide k-blocks
+  int kb_per_split;  // k-blocks per gridDim.z slice
+  const float* bias;
+  const float* mask;
+  int64_t ldmask;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const TcGemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * G_BM;
+  const int kb0 = blockIdx.z * g.kb_per_split;
+  const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+  const int nkb = kb1 - kb0;  // host guarantees >= 1
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);  // BN fp32 accumulator columns (power of two >= 32)
+  fence_before_thread_sync();
+  __syncthreads();
+  fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        const int k0 = (kb0 + i) * G_BK;
+        if (A_MN) tma_load_3d(sa, &map_a, &full_bar[s], 0, k0, m0 / 32);
+        else      tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);
+        if (B_MN) tma_load_3d(sb, &map_b, &full_bar[s], 0, k0, n0 / 32);
+        else      tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(FMT_TF32, G_BM, BN, A_MN, B_MN);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        fence_after_thread_sync();
+        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < G_BK / 8; ++k) {
+          // K-major: advance 8 floats (32 B) inside the 128-B swizzle row; MN-major: next 8 k-rows (1024 B)
+          const uint64_t da = A_MN ? make_smem_desc(sa + k * 1024, G_BK * 128, 1024, UMMA_SWIZZLE_128B)
+                                   : make_smem_desc(sa + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
+          const uint64_t db = B_MN ? make_smem_desc(sb + k * 1024, G_BK * 128, 1024, UMMA_SWIZZLE_128B)
+                                   : make_smem_desc(sb + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
+          mma_tf32(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+      }
+      mma_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    fence_after_thread_sync();
+    const bool row_ok = row < g.M;
+    float* crow = g.C + (int64_t)row * g.ldc;
+    const float* mrow = (g.epi == 3) ? g.mask + (int64_t)row * g.ldmask : nullptr;
+    const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (n0 + c >= g.N) break;  // warp-uniform
+      float v[32];
+      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + c + j;
+          if (n < g.N) {
+            float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
+            if (!g.atomic) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (n + e < g.N) {
+                  if (g.epi == 1 || g.epi == 2) o[e] += __ldg(g.bias + n + e);
+                  if (g.epi == 2) o[e] = (o[e] < 0.f) ? 0.f : o[e];
+                  if (g.epi == 3) o[e] = (__ldg(mrow + n + e) <= 0.f) ? 0.f : o[e];
+                }
+              }
+            }
+            if (n + 3 < g.N && vec_ok) {
+              if (g.atomic) red_add_v4(crow + n, o[0], o[1], o[2], o[3]);
+              else *reinterpret_cast<float4*>(crow + n) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (n + e < g.N) {
+                  if (g.atomic) atomicAdd(crow + n + e, o[e]);
+                  else crow[n + e] = o[e];
+                }
+            }
+          }
+        }
+      }
+    }
+  }
+  fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_thread_sync();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline int resolve_encode_tiled(pycnn_b200_ctx* c) {
+  if (c->encode_tiled) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  PB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  PB_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+  c->encode_tiled = fn;
+  return 0;
+}
+
+// K-major operand: matrix [rows, K] row-major with pitch ld (floats).  Box {32 floats, box_rows}.
+static inline int make_map_kmajor(pycnn_b200_ctx* c, CUtensorMap* map, const float* base, int64_t rows, int64_t K,
+                                  int64_t ld, int box_rows) {
+  PB_TRY(resolve_encode_tiled(c));
+  PB_CHECK((ld & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand needs 16-byte aligned rows (ld=%lld)", (long long)ld);
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(c->encode_tiled)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(K-major rows=%lld K=%lld ld=%lld) failed: %d", (long long)rows, (long long)K, (long long)ld, (int)r);
+  return 0;
+}
+
+// MN-major operand: matrix [K, MN] row-major with pitch ld.  Viewed as 3-D {32, K, ceil(MN/32)} with
+// strides {ld*4, 128} bytes so one box {32, 32, box_atoms} lands as [atom][k][32 floats] in smem.
+static inline int make_map_mnmajor(pycnn_b200_ctx* c, CUtensorMap* map, const float* base, int64_t K, int64_t MN,
+                                   int64_t ld, int box_atoms) {
+  PB_TRY(resolve_encode_tiled(c));
+  PB_CHECK((ld & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand needs 16-byte aligned rows (ld=%lld)", (long long)ld);
+  cuuint64_t dims[3] = {32, (cuuint64_t)K, (cuuint64_t)ceil_div(MN, 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
+  cuuint32_t box[3] = {32, 32, (cuuint32_t)box_atoms};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(c->encode_tiled)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(MN-major K=%lld MN=%lld ld=%lld) failed: %d", (long long)K, (long long)MN, (long long)ld, (int)r);
+  return 0;
+}
+
+struct GemmCall {
+  const float* A; int64_t lda; bool a_kmajor;  // kmajor: [M,K] row-major; else [K,M] row-major
+  const float* B; int64_t ldb; bool b_kmajor;  // kmajor: [N,K] row-major; else [K,N] row-major
+  float* C; int64_t ldc;
+  int M, N, K;
+  int epi;
+  const float* bias;
+  const float* mask; int64_t ldmask;
+  int cls;  // KernelClass
+};
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc_gemm(pycnn_b200_ctx* c, const GemmCall& g, const CUtensorMap& ma, const CUtensorMap& mb,
+                          const tc::TcGemmArgs& args, dim3 grid) {
+  using Cfg = tc::GemmCfg<BN>;
+  static bool attr_set[16] = {};
+  auto kern = tc::gemm_tf32_kernel<BN, A_MN, B_MN>;
+  if (!attr_set[c->device & 15]) {
+    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[c->device & 15] = true;
+  }
+  kern<<<grid, 192, Cfg::SMEM_BYTES, c->stream>>>(ma, mb, args);
+  PB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <bool A_MN, bool B_MN>
+static int dispatch_bn(pycnn_b200_ctx* c, int BN, const GemmCall& g, const CUtensorMap& ma, const CUtensorMap& mb,
+                       const tc::TcGemmArgs& args, dim3 grid) {
+  switch (BN) {
+    case 32: return launch_tc_gemm<32, A_MN, B_MN>(c, g, ma, mb, args, grid);
+    case 64: return launch_tc_gemm<64, A_MN, B_MN>(c, g, ma, mb, args, grid);
+    case 128: return launch_tc_gemm<128, A_MN, B_MN>(c, g, ma, mb, args, grid);
+    default: return launch_tc_gemm<256, A_MN, B_MN>(c, g, ma, mb, args, grid);
+  }
+}
+
+static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
+  PB_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "tc_gemm: empty problem");
+  PB_CHECK(!( !g.a_kmajor && g.b_kmajor), "tc_gemm: (A MN-major, B K-major) is not instantiated");
+  const int BN = g.N <= 32 ? 32 : g.N <= 64 ? 64 : g.N <= 128 ? 128 : 256;
+  const int tiles_m = (int)ceil_div(g.M, tc::G_BM), tiles_n = (int)ceil_div(g.N, BN);
+  const int num_kb = (int)ceil_div(g.K, tc::G_BK);
+  // split-K when the tile grid cannot fill the 148 SMs and K is deep enough to amortise the atomics
+  int split = 1;
+  const int tiles = tiles_m * tiles_n;
+  if (tiles * 2 <= c->num_sms && num_kb >= 16) {
+    split = (int)std::min<int64_t>(c->num_sms / tiles, num_kb / 8);
+    if (split < 1) split = 1;
+  }
+  int kb_per_split = (int)ceil_div(num_kb, split);
+  split = (int)ceil_div(num_kb, kb_per_split);  // no empty slices
+  CUtensorMap ma, mb;
+  if (g.a_kmajor) PB_TRY(make_map_kmajor(c, &ma, g.A, g.M, g.K, g.lda, tc::G_BM));
+  else            PB_TRY(make_map_mnmajor(c, &ma, g.A, g.K, g.M, g.lda, tc::G_BM / 32));
+  if (g.b_kmajor) PB_TRY(make_map_kmajor(c, &mb, g.B, g.N, g.K, g.ldb, BN));
+  else            PB_TRY(make_map_mnmajor(c, &mb, g.B, g.K, g.N, g.ldb, BN / 32));
+  tc::TcGemmArgs a;
+  a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.N = g.N; a.K = g.K;
+  a.epi = g.epi; a.atomic = split > 1 ? 1 : 0;
+  a.num_kb = num_kb; a.kb_per_split = kb_per_split;
+  a.bias = g.bias; a.mask = g.mask; a.ldmask = g.ldmask;
+  dim3 grid(tiles_n, tiles_m, split);
+  if (split > 1) {
+    LaunchScope ls(c, KC_MISC);
+    PB_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * ((size_t)(g.M - 1) * g.ldc + g.N), c->stream));
+  }
+  {
+    LaunchScope ls(c, g.cls);
+    if (g.a_kmajor && g.b_kmajor) PB_TRY((dispatch_bn<false, false>(c, BN, g, ma, mb, a, grid)));
+    else if (g.a_kmajor && !g.b_kmajor) PB_TRY((dispatch_bn<false, true>(c, BN, g, ma, mb, a, grid)));
+    else PB_TRY((dispatch_bn<true, true>(c, BN, g, ma, mb, a, grid)));
+  }
+  if (split > 1 && g.epi != 0) {
+    LaunchScope ls(c, KC_MISC);
+    const int64_t total = (int64_t)g.M * g.N;
+    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 8 * c->num_sms);
+    gemm_fixup_kernel<<<blocks, 256, 0, c->stream>>>(g.C, g.M, g.N, g.ldc, g.epi, g.bias, g.mask, g.ldmask);
+    PB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace pb

@@ -1,0 +1,113 @@
+"""Data-parallel host logic: one process per GPU (torchrun), NCCL owned by libpycnn_b200.so.
+
+The reference has no parallelism of any kind.  The hot path shards per batch:
+every rank holds the same device dataset, takes a contiguous 1/W slice of each batch of the shared
+permutation, and the flat float32 gradient buffer is all-reduced with ncclSum once per step -- the
+reference's gradients are batch SUMS (backward_pass.pyx:71-72,92-93), so no 1/W scaling is needed
+and the reduced gradient equals the single-device gradient.  Feature extraction and prediction shard
+per image with no collective.
+
+torch.distributed is plumbing only: it carries the 128-byte ncclUniqueId from rank 0 to the other
+ranks (any backend: nccl on the GPU box, gloo in the CPU tests) and the final scalar reductions of
+embarrassingly-parallel jobs.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def batch_slice(start: int, end: int, rank: int, world: int):
+    """The slice of batch [start, end) that `rank` processes: contiguous ceil(len/W) chunks.
+    Mirrors pycnn_b200_train_epoch (pycnn_b200/csrc/api.cu); ranks past the end get an empty slice."""
+    length = end - start
+    per = -(-length // world)
+    lo, hi = min(length, per * rank), min(length, per * (rank + 1))
+    return start + lo, start + hi
+
+
+def image_shard(n: int, rank: int, world: int):
+    """Contiguous N/W image range per rank for extraction / batched predict (no collective)."""
+    per = -(-n // world)
+    return min(n, per * rank), min(n, per * (rank + 1))
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_process_group(backend=None):
+    """Initialise torch.distributed from the torchrun environment (idempotent)."""
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            import torch
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            import torch
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def broadcast_bytes(payload: bytes | None, src: int = 0) -> bytes:
+    """Broadcast a small byte string from `src` over the default process group."""
+    import torch.distributed as dist
+    box = [payload]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def attach(model, make_unique_id=None):
+    """Join `model` (a cuda(True) PyCNN) to the job's NCCL communicator.  No-op for world == 1."""
+    from . import _lib
+    rank, world, _ = dist_env()
+    model._rank, model._world = rank, world
+    if world == 1:
+        return rank, world
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        init_process_group()
+    uid = (make_unique_id or _lib.comm_unique_id)() if rank == 0 else None
+    uid = broadcast_bytes(uid, src=0)
+    model._require().comm_init(uid, rank, world)
+    return rank, world
+
+
+def allreduce_scalars(values, op="sum"):
+    """Sum (or max) a few python floats over all ranks; identity for world == 1."""
+    rank, world, _ = dist_env()
+    if world == 1:
+        return list(values)
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(list(values), dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX)
+    return t.cpu().tolist()
+
+
+class ShardedStepper:
+    """Reference implementation of the sharded step with a pluggable compute + all-reduce, used by the
+    world_size-2 gloo tests to pin the host logic (slice arithmetic, sum-not-mean reduction, identical
+    update on every rank) without a GPU.  `grad_fn(idx) -> (flat_grad, loss_sum, correct)`;
+    `allreduce(array) -> array`; `update_fn(flat_grad)`."""
+
+    def __init__(self, rank, world, grad_fn, allreduce, update_fn):
+        self.rank, self.world = rank, world
+        self.grad_fn, self.allreduce, self.update_fn = grad_fn, allreduce, update_fn
+
+    def epoch(self, perm, batch_size):
+        n = len(perm)
+        totals = np.zeros(2)
+        for start in range(0, n, batch_size):
+            end = min(start + batch_size, n)
+            lo, hi = batch_slice(start, end, self.rank, self.world)
+            g, loss, correct = self.grad_fn(perm[lo:hi])
+            g = self.allreduce(g)
+            self.update_fn(g)
+            totals += (loss, correct)
+        totals = self.allreduce(totals)
+        return float(totals[0]), int(round(totals[1]))

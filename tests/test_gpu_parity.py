@@ -1,0 +1,426 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (pycnn_b200/_lib.py is a 1:1 ctypes
+binding of include/pycnn_b200.h), against the CPU oracle and the committed reference goldens.
+
+Tolerances (north star): FP32-SIMT mode 1e-5, TF32 mode 1e-2, both as max|a-b|/max|b| per tensor
+(tests/helpers.rel_err; SURVEY.md section 7 "Tolerance metric"); predicted classes bit-exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import pycnn_oracle as O
+from tests.helpers import custom_filters, load_golden, rel_err, synth_images, synth_labels
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+TF32_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pycnn_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+@pytest.fixture()
+def ctx(lib):
+    c = lib.Context(0)
+    yield c
+    c.close()
+
+
+EXTRACT_MODES = ["simt", "tc"]
+
+
+def _set_extract(lib, ctx, mode):
+    ctx.set_extract_mode(lib.EXTRACT_SIMT if mode == "simt" else lib.EXTRACT_TC)
+
+
+# ------------------------------------------------------------------------------------------ extractor
+@pytest.mark.parametrize("mode", EXTRACT_MODES)
+@pytest.mark.parametrize("tag", ["s32", "s33", "s64", "s7"])
+def test_extract_matches_reference_golden(lib, ctx, mode, tag):
+    g = load_golden("extract.npz")
+    _set_extract(lib, ctx, mode)
+    imgs = g[f"{tag}_images"]
+    for name, filt in (("default", O.DEFAULT_FILTERS), ("custom", g["custom_filters"].tolist())):
+        ctx.set_filters(filt)
+        got = ctx.extract(imgs)
+        want = g[f"{tag}_{name}"]
+        assert got.shape == want.shape
+        assert rel_err(got, want) < FP32_TOL, (mode, tag, name, rel_err(got, want))
+        got32 = ctx.extract(imgs, dtype=np.float32)
+        np.testing.assert_array_equal(got32.astype(np.float64), got)
+
+
+@pytest.mark.parametrize("mode", EXTRACT_MODES)
+def test_extract_edge_cases(lib, ctx, mode):
+    _set_extract(lib, ctx, mode)
+    ctx.set_filters(O.DEFAULT_FILTERS)
+    # empty batch
+    assert ctx.extract(np.zeros((0, 32, 32, 3), np.uint8)).shape == (0, 4275)
+    # smallest legal image (4x4 -> one pooled output per filter), extreme pixel values
+    for fill in (0, 255):
+        img = np.full((1, 4, 4, 3), fill, np.uint8)
+        np.testing.assert_allclose(ctx.extract(img)[0], O.extract_features(img[0]), atol=2e-5)
+    # a ragged batch size that is not a multiple of any tile, odd image size, single filter
+    ctx.set_filters([O.DEFAULT_FILTERS[18]])
+    imgs = synth_images(37, 21, seed=3)
+    assert rel_err(ctx.extract(imgs), O.extract_batch(imgs, [O.DEFAULT_FILTERS[18]])) < FP32_TOL
+    # the reference's test_06 input (tests/test.py:85-94)
+    g = load_golden("extract.npz")
+    red = np.zeros((32, 32, 3), np.uint8)
+    red[..., 0] = 255
+    ctx.set_filters(O.DEFAULT_FILTERS[:3])
+    assert rel_err(ctx.extract(red)[0], g["red_first3"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("mode", EXTRACT_MODES)
+def test_extract_full_size_properties(lib, ctx, mode):
+    """BASELINE-sized batch (4096 x 32x32): batch independence, a sampled oracle check, and
+    positive homogeneity in the taps (ReLU/max-pool commute with a positive scale)."""
+    _set_extract(lib, ctx, mode)
+    ctx.set_filters(O.DEFAULT_FILTERS)
+    imgs = synth_images(4096, 32, seed=0)
+    full = ctx.extract(imgs, dtype=np.float32)
+    rows = np.random.default_rng(5).choice(4096, 48, replace=False)
+    assert rel_err(full[rows], O.extract_batch(imgs[rows])) < FP32_TOL
+    np.testing.assert_array_equal(ctx.extract(imgs[rows], dtype=np.float32), full[rows])
+    ctx.set_filters((2.0 * np.asarray(O.DEFAULT_FILTERS)).tolist())
+    doubled = ctx.extract(imgs[:256], dtype=np.float32)
+    assert rel_err(doubled, 2.0 * full[:256].astype(np.float64)) < FP32_TOL
+    # larger image through the tiled path
+    big = synth_images(2, 224, seed=9)
+    ctx.set_filters(O.DEFAULT_FILTERS)
+    assert rel_err(ctx.extract(big), O.extract_batch(big)) < FP32_TOL
+
+
+def test_optimized_cpp_dropins(ctx):
+    """softmax / cross_entropy / max_pool on the GPU vs optimized.cpp + max_pooling.pyx semantics."""
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(7, 13)) * 5
+    np.testing.assert_allclose(ctx.softmax(x), O.softmax(x), atol=1e-14)
+    np.testing.assert_allclose(ctx.softmax(np.array([[1.0, 2, 3], [4, 5, 6]])).sum(1), [1, 1], atol=1e-12)
+    p = O.softmax(x)
+    y = O.one_hot(rng.integers(0, 13, 7), 13)
+    np.testing.assert_allclose(ctx.cross_entropy(p, y), O.cross_entropy(p, y), rtol=1e-13)
+    fm = np.arange(1, 17, dtype=float).reshape(4, 4)
+    np.testing.assert_array_equal(ctx.max_pool(fm), [[6, 8], [14, 16]])       # tests/test.py:164-181
+    fm = rng.normal(size=(31, 30))
+    np.testing.assert_array_equal(ctx.max_pool(fm), O.max_pool2x2(fm))
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [(128, 256, 64), (4096 // 8, 256, 4275), (32, 10, 64), (200, 100, 1000), (256, 4275, 512), (77, 33, 45),
+               (128, 64, 8), (300, 513, 96)]
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", FP32_TOL), ("tf32", 2e-3)])
+@pytest.mark.parametrize("layout", [(1, 1), (1, 0), (0, 0)])
+@pytest.mark.parametrize("shape", GEMM_SHAPES)
+def test_gemm_probe_all_layouts(lib, ctx, mode, tol, layout, shape):
+    """forward (K-major/K-major), dA (K-major/MN-major) and dW (MN-major/MN-major) operand forms."""
+    ctx.set_math_mode(lib.MATH_FP32_SIMT if mode == "fp32" else lib.MATH_TF32)
+    M, N, K = shape
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.normal(size=(M, K)).astype(np.float32)
+    B = rng.normal(size=(N, K)).astype(np.float32)
+    a_k, b_k = layout
+    C, _ = ctx.gemm_probe(A if a_k else np.ascontiguousarray(A.T), B if b_k else np.ascontiguousarray(B.T),
+                          a_kmajor=bool(a_k), b_kmajor=bool(b_k))
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+    assert rel_err(C, want) < tol, (mode, layout, shape, rel_err(C, want))
+
+
+# ------------------------------------------------------------------------------------------ MLP
+def _load_small(ctx, lib, g, opt, lr, mode):
+    layers = g["layers"].tolist()
+    D, C = int(g["D"]), int(g["C"])
+    ctx.set_math_mode(lib.MATH_FP32_SIMT if mode == "fp32" else lib.MATH_TF32)
+    ctx.set_network(D, layers, C)
+    wk, bk = O.layer_keys(len(layers))
+    for l, (w, b) in enumerate(zip(wk, bk)):
+        ctx.set_param(2 * l, g[f"{opt}_init_{w}"])
+        ctx.set_param(2 * l + 1, g[f"{opt}_init_{b}"])
+    ctx.set_optimizer(lib.OPT_ADAM if opt == "adam" else lib.OPT_SGD, lr)
+    return layers, D, C, wk, bk
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", FP32_TOL), ("tf32", TF32_TOL)])
+@pytest.mark.parametrize("opt,lr", [("sgd", 0.05), ("adam", 0.01)])
+def test_mlp_small_forward_backward_update(lib, ctx, mode, tol, opt, lr):
+    """forward_pass / backward_pass / gradient_decent against goldens from the reference itself."""
+    g = load_golden("mlp_small.npz")
+    layers, D, C, wk, bk = _load_small(ctx, lib, g, opt, lr, mode)
+    data, lab, bs = g["data"], g["labels"], int(g["bs"])
+    N = len(data)
+    ctx.dataset_alloc(N)
+    ctx.dataset_set_features(0, data)
+    ctx.dataset_set_labels(0, lab)
+    np.testing.assert_allclose(ctx.dataset_get_features(0, N), data.astype(np.float32).astype(np.float64))
+    idx0 = np.arange(0, bs) % N
+    probs = ctx.forward_rows(idx=idx0)
+    assert rel_err(probs, g[f"{opt}_probs0"]) < tol
+    assert np.array_equal(probs.argmax(1), g[f"{opt}_probs0"].argmax(1))
+    # same through host features
+    assert rel_err(ctx.forward_features(data[idx0]), g[f"{opt}_probs0"]) < tol
+    ctx.backward_last(lab[idx0])
+    for l, (w, b) in enumerate(zip(wk, bk)):
+        assert rel_err(ctx.get_grad(2 * l), g[f"{opt}_grad0_{w}"]) < tol, w
+        assert rel_err(ctx.get_grad(2 * l + 1), g[f"{opt}_grad0_{b}"]) < tol, b
+    losses = []
+    for step in range(5):
+        idx = np.arange(step * 3, step * 3 + bs) % N
+        ls, _ = ctx.train_step(idx)
+        losses.append(ls)
+    loss_tol = 1e-5 if mode == "fp32" else 1e-2
+    np.testing.assert_allclose(losses, g[f"{opt}_step_losses"], rtol=loss_tol)
+    for l, (w, b) in enumerate(zip(wk, bk)):
+        assert rel_err(ctx.get_param(2 * l), g[f"{opt}_after5_{w}"]) < tol, w
+        assert rel_err(ctx.get_param(2 * l + 1), g[f"{opt}_after5_{b}"]) < tol, b
+    assert ctx.step_count() == 0     # CPU rule: t never advances
+
+
+@pytest.mark.parametrize("opt,lr", [("sgd", 0.05), ("adam", 0.01)])
+def test_train_epoch_short_last_batch(lib, ctx, opt, lr):
+    """3 epochs, N=20, bs=8 (8+8+4) against the reference's train_model result (golden)."""
+    g = load_golden("mlp_small.npz")
+    layers, D, C, wk, bk = _load_small(ctx, lib, g, opt, lr, "fp32")
+    data, lab, bs = g["data"], g["labels"], int(g["bs"])
+    ctx.dataset_alloc(len(data))
+    ctx.dataset_set_features(0, data)
+    ctx.dataset_set_labels(0, lab)
+    O.init_layers(D, layers, C, seed=42)              # advance the host stream exactly like the reference
+    w, b = O.init_layers(D, layers, C, seed=42)
+    res = O.train_epochs(data, O.one_hot(lab, C), w, b, layers, lr, opt, bs, epochs=3)
+    for e in range(3):
+        loss, correct = ctx.train_epoch(res["perms"][e], bs)
+        assert abs(loss / len(data) - res["epoch_loss"][e]) < 1e-5 * max(1, res["epoch_loss"][e])
+        assert correct == res["epoch_correct"][e]
+    for l, (wn, bn) in enumerate(zip(wk, bk)):
+        assert rel_err(ctx.get_param(2 * l), g[f"{opt}_trained_{wn}"]) < 1e-4
+        assert rel_err(ctx.get_param(2 * l + 1), g[f"{opt}_trained_{bn}"]) < 1e-4
+
+
+def test_cupy_update_rule_and_nan_skip(lib, ctx):
+    """The alternative CuPy rule (t advances, no clip) and the CPU rule's NaN/Inf skip."""
+    g = load_golden("mlp_small.npz")
+    layers, D, C, wk, bk = _load_small(ctx, lib, g, "adam", 0.01, "fp32")
+    data, lab, bs = g["data"], g["labels"], int(g["bs"])
+    ctx.dataset_alloc(len(data))
+    ctx.dataset_set_features(0, data)
+    ctx.dataset_set_labels(0, lab)
+    ctx.set_update_rule(lib.RULE_CUPY)
+    w = {k: g[f"adam_init_{k}"].copy() for k in wk}
+    b = {k: g[f"adam_init_{k}"].copy() for k in bk}
+    m = {k: np.zeros_like(v) for k, v in {**w, **b}.items()}
+    v = {k: np.zeros_like(v_) for k, v_ in {**w, **b}.items()}
+    y = O.one_hot(lab, C)
+    t = 0
+    for step in range(4):
+        idx = np.arange(step * 3, step * 3 + bs) % len(data)
+        ctx.train_step(idx)
+        _, _, t = O.train_step(data[idx], y[idx], w, b, layers, 0.01, "adam", m, v, rule="cupy", t=t)
+    assert ctx.step_count() == 4
+    for l, k in enumerate(wk):
+        assert rel_err(ctx.get_param(2 * l), w[k]) < 1e-4, k
+    # NaN gradient -> CPU rule leaves that tensor untouched (gradient_decent.pyx:37-39)
+    ctx.set_update_rule(lib.RULE_CPU)
+    ctx.set_optimizer(lib.OPT_SGD, 0.05)
+    bad = data.copy()
+    bad[0, 0] = np.nan
+    ctx.dataset_set_features(0, bad)
+    before = [ctx.get_param(i) for i in range(ctx.num_params())]
+    ctx.train_step(np.arange(bs))
+    after = [ctx.get_param(i) for i in range(ctx.num_params())]
+    for a, bb in zip(after, before):
+        np.testing.assert_array_equal(a, bb)      # every tensor's gradient is NaN-poisoned -> all skipped
+
+
+@pytest.mark.parametrize("mode,loss_tol", [("fp32", 2e-4), ("tf32", 2e-2)])
+@pytest.mark.parametrize("opt,lr", [("sgd", 1e-3), ("adam", 1e-4)])
+def test_c1_trajectory_100_steps(lib, ctx, mode, loss_tol, opt, lr):
+    """BASELINE config 1 (32x32, 10 classes, [256,128,64], bs 32): 100-step loss trajectory and final
+    predictions against the reference's own run (tests/golden/traj_c1.npz), extractor included."""
+    g = load_golden("traj_c1.npz")
+    S, C, bs, N, steps = int(g["S"]), int(g["C"]), int(g["bs"]), int(g["N"]), int(g["steps"])
+    layers = g["layers"].tolist()
+    ctx.set_math_mode(lib.MATH_FP32_SIMT if mode == "fp32" else lib.MATH_TF32)
+    ctx.set_extract_mode(lib.EXTRACT_SIMT if mode == "fp32" else lib.EXTRACT_TC)
+    ctx.set_filters(O.DEFAULT_FILTERS)
+    D = ctx.feature_count(S)
+    ctx.set_network(D, layers, C)
+    w, b = O.init_layers(D, layers, C, seed=42)
+    wk, bk = O.layer_keys(len(layers))
+    for l, (wn, bn) in enumerate(zip(wk, bk)):
+        ctx.set_param(2 * l, w[wn])
+        ctx.set_param(2 * l + 1, b[bn])
+    ctx.set_optimizer(lib.OPT_ADAM if opt == "adam" else lib.OPT_SGD, lr)
+    ctx.dataset_alloc(N)
+    ctx.dataset_extract(0, synth_images(N, S, 0))
+    ctx.dataset_set_labels(0, synth_labels(N, C, 1))
+    feats = ctx.dataset_get_features(0, N)
+    d = g["feat_digest"]
+    np.testing.assert_allclose([feats.sum(), np.abs(feats).sum(), feats.max(), feats[123, 456], feats[2047, 4274]],
+                               d, rtol=1e-5)
+    losses, corrects, step = [], [], 0
+    while step < steps:
+        perm = np.random.permutation(N)        # host stream continues after seed 42 + init, like the reference
+        if step == 0:
+            np.testing.assert_array_equal(perm[:64], g[f"{opt}_perm0_head"])
+        for start in range(0, N, bs):
+            ls, c = ctx.train_step(perm[start:start + bs])
+            losses.append(ls)
+            corrects.append(c)
+            step += 1
+            if step >= steps:
+                break
+    want = g[f"{opt}_step_losses"]
+    err = np.abs(np.array(losses) - want) / want
+    print(f"\n[{mode}/{opt}] 100-step loss trajectory: max rel dev {err.max():.3e}, final {losses[-1]:.6f} vs {want[-1]:.6f}")
+    assert err.max() < loss_tol
+    if mode == "fp32":
+        assert np.mean(np.array(corrects) == g[f"{opt}_step_correct"]) >= 0.97   # near-tie flips only
+    probs = ctx.forward_rows(row0=0, bs=64)
+    want_p = g[f"{opt}_probs_first64"]
+    assert rel_err(probs, want_p) < (1e-4 if mode == "fp32" else 5e-2)
+    if mode == "fp32":
+        np.testing.assert_array_equal(probs.argmax(1), want_p.argmax(1))       # bit-exact classes
+    else:
+        gap = np.sort(want_p, axis=1)
+        near_tie = (gap[:, -1] - gap[:, -2]) < 2e-2
+        assert np.all((probs.argmax(1) == want_p.argmax(1)) | near_tie)
+
+
+def test_shard_sum_equals_full_batch_gradient(lib, ctx):
+    """The data-parallel identity on one GPU: grads of two half batches add up to the full-batch
+    gradient (sums, no 1/W scaling) -- what ncclSum over ranks reproduces."""
+    g = load_golden("mlp_small.npz")
+    layers, D, C, wk, bk = _load_small(ctx, lib, g, "sgd", 0.05, "fp32")
+    data, lab = g["data"], g["labels"]
+    ctx.dataset_alloc(len(data))
+    ctx.dataset_set_features(0, data)
+    ctx.dataset_set_labels(0, lab)
+    idx = np.arange(16)
+    ctx.forward_backward(idx)
+    full = [ctx.get_grad(i) for i in range(ctx.num_params())]
+    ctx.forward_backward(idx[:8])
+    a = [ctx.get_grad(i) for i in range(ctx.num_params())]
+    ctx.forward_backward(idx[8:])
+    b = [ctx.get_grad(i) for i in range(ctx.num_params())]
+    for f, x, y in zip(full, a, b):
+        assert rel_err(x + y, f) < 1e-5
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("tf32", TF32_TOL)])
+def test_config2_full_size_step_properties(lib, ctx, mode, tol):
+    """BASELINE config 2 shapes (D=4275, [256,128,64], bs=4096): one step's gradients against the
+    oracle on the same inputs, order invariance of the batch sum, and idempotent inference."""
+    S, C, layers, bs = 32, 10, [256, 128, 64], 4096
+    ctx.set_math_mode(lib.MATH_FP32_SIMT if mode == "fp32" else lib.MATH_TF32)
+    ctx.set_filters(O.DEFAULT_FILTERS)
+    D = ctx.feature_count(S)
+    ctx.set_network(D, layers, C)
+    w, b = O.init_layers(D, layers, C, seed=42)
+    wk, bk = O.layer_keys(len(layers))
+    for l, (wn, bn) in enumerate(zip(wk, bk)):
+        ctx.set_param(2 * l, w[wn])
+        ctx.set_param(2 * l + 1, b[bn])
+    imgs, lab = synth_images(bs, S, 0), synth_labels(bs, C, 1)
+    ctx.dataset_alloc(bs)
+    ctx.dataset_extract(0, imgs)
+    ctx.dataset_set_labels(0, lab)
+    feats = ctx.dataset_get_features(0, bs)
+    idx = np.random.default_rng(0).permutation(bs)
+    ctx.forward_backward(idx)
+    grads = [ctx.get_grad(i) for i in range(ctx.num_params())]
+    p, acts, _ = O.forward(feats[idx], w, b, layers)
+    gw, gb = O.backward(p, O.one_hot(lab[idx], C), acts, w, layers)
+    for l, (wn, bn) in enumerate(zip(wk, bk)):
+        assert rel_err(grads[2 * l], gw[wn]) < tol, (wn, rel_err(grads[2 * l], gw[wn]))
+        assert rel_err(grads[2 * l + 1], gb[bn]) < tol, bn
+    ctx.forward_backward(idx[::-1].copy())
+    for a, bb in zip(grads, [ctx.get_grad(i) for i in range(ctx.num_params())]):
+        assert rel_err(a, bb) < 1e-4
+    p1 = ctx.forward_rows(row0=0, bs=512)
+    p2 = ctx.forward_rows(row0=0, bs=512)
+    np.testing.assert_array_equal(p1, p2)
+    assert rel_err(p1, O.forward(feats[:512], w, b, layers)[0]) < tol
+
+
+def test_streamed_image_step_equals_resident_step(lib, ctx):
+    """train_step_images (H2D + extractor + step) == dataset_extract + train_step on the same batch."""
+    S, C, layers, bs = 32, 10, [64, 32], 256
+    imgs, lab = synth_images(bs, S, 3), synth_labels(bs, C, 4)
+    results = []
+    for streamed in (False, True):
+        ctx.set_math_mode(lib.MATH_FP32_SIMT)
+        ctx.set_filters(O.DEFAULT_FILTERS)
+        D = ctx.feature_count(S)
+        ctx.set_network(D, layers, C)
+        w, b = O.init_layers(D, layers, C, seed=42)
+        wk, bk = O.layer_keys(len(layers))
+        for l, (wn, bn) in enumerate(zip(wk, bk)):
+            ctx.set_param(2 * l, w[wn])
+            ctx.set_param(2 * l + 1, b[bn])
+        ctx.set_optimizer(lib.OPT_ADAM, 1e-3)
+        if streamed:
+            stats = ctx.train_step_images(imgs, lab)
+        else:
+            ctx.dataset_alloc(bs)
+            ctx.dataset_extract(0, imgs)
+            ctx.dataset_set_labels(0, lab)
+            stats = ctx.train_step(np.arange(bs))
+        results.append((stats, [ctx.get_param(i) for i in range(ctx.num_params())]))
+    assert results[0][0][1] == results[1][0][1]
+    assert abs(results[0][0][0] - results[1][0][0]) < 1e-6 * abs(results[0][0][0])
+    for a, bb in zip(results[0][1], results[1][1]):
+        np.testing.assert_allclose(a, bb, rtol=0, atol=1e-7)
+
+
+def test_predict_and_evaluate_images(lib, ctx):
+    S, C, layers, n = 32, 10, [64, 32], 300
+    ctx.set_math_mode(lib.MATH_FP32_SIMT)
+    ctx.set_filters(O.DEFAULT_FILTERS)
+    D = ctx.feature_count(S)
+    ctx.set_network(D, layers, C)
+    w, b = O.init_layers(D, layers, C, seed=42)
+    wk, bk = O.layer_keys(len(layers))
+    for l, (wn, bn) in enumerate(zip(wk, bk)):
+        ctx.set_param(2 * l, w[wn])
+        ctx.set_param(2 * l + 1, b[bn])
+    imgs, lab = synth_images(n, S, 5), synth_labels(n, C, 6)
+    feats = O.extract_batch(imgs)
+    p, _, _ = O.forward(feats, w, b, layers)
+    cls, conf = ctx.predict_images(imgs)
+    np.testing.assert_array_equal(cls, p.argmax(1))
+    np.testing.assert_allclose(conf, p.max(1), rtol=1e-4)
+    loss, correct, pred = ctx.evaluate_images(imgs, lab, 64)
+    np.testing.assert_array_equal(pred, p.argmax(1))
+    assert correct == int((p.argmax(1) == lab).sum())
+    assert abs(loss - O.cross_entropy(p, O.one_hot(lab, C)).sum()) < 1e-4 * loss
+    ctx.dataset_alloc(n)
+    ctx.dataset_extract(0, imgs)
+    ctx.dataset_set_labels(0, lab)
+    loss2, correct2, pred2 = ctx.evaluate_rows(0, n, 64)
+    assert correct2 == correct and abs(loss2 - loss) < 1e-9 * loss
+    np.testing.assert_array_equal(pred2, pred)
+
+
+def test_error_reporting(lib, ctx):
+    with pytest.raises(lib.BackendError, match="set_filters"):
+        ctx.extract(np.zeros((1, 8, 8, 3), np.uint8))
+    ctx.set_filters(O.DEFAULT_FILTERS)
+    with pytest.raises(lib.BackendError):
+        ctx.dataset_alloc(4)                      # no network yet
+    ctx.set_network(4275, [8], 3)
+    ctx.dataset_alloc(4)
+    with pytest.raises(lib.BackendError, match="label"):
+        ctx.dataset_set_labels(0, np.array([0, 1, 2, 3]))
+    with pytest.raises(lib.BackendError, match="features"):
+        ctx.dataset_extract(0, np.zeros((1, 16, 16, 3), np.uint8))
+    with pytest.raises(lib.BackendError, match="out of range"):
+        ctx.train_step(np.array([0, 99]))
+    with pytest.raises(lib.BackendError):
+        lib.Context(99)

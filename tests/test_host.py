@@ -1,0 +1,203 @@
+"""CPU tier: the C-ABI library loads and exports every declared symbol, the host logic (model.bin
+layout, batch sharding, world_size-2 gloo all-reduce of shard gradients) is right, and the product
+refuses to run without a GPU instead of falling back."""
+import contextlib
+import io
+import os
+import pickle
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from oracle import pycnn_oracle as O
+from pycnn_b200 import PyCNN, _lib, parallel
+from tests.helpers import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = _lib.load()
+    names = _lib.header_symbols()
+    assert len(names) >= 50
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pycnn_b200.h but not exported"
+    assert set(names) == set(_lib._SIGNATURES), "ctypes binding and header disagree"
+    assert lib.pycnn_b200_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(names) <= exported
+
+
+def test_library_is_sm100a_tcgen05_tma():
+    """The shipped binary carries Blackwell tensor-core / TMA SASS (UTC*MMA, UTMALDG, LDTM)."""
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass or "SM100" in sass.upper()
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+def _gpu_present():
+    try:
+        return _lib.device_count() > 0
+    except _lib.BackendError:
+        return False
+
+
+def test_no_cpu_fallback():
+    m = PyCNN()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.init(layers=[8])
+    assert m.use_cuda is False and m.optimizer == "sgd"
+    with pytest.raises(RuntimeError, match="cuda\\(True\\)"):
+        m._softmax_batch(np.ones((2, 3)))
+    with pytest.raises(RuntimeError):
+        m._preprocess_image(np.zeros((8, 8, 3), np.uint8), 8, m.filters)
+    if not _gpu_present():
+        with pytest.raises(_lib.BackendError, match="no CPU fallback"):
+            m.cuda(True)
+        assert m.use_cuda is False
+
+
+def test_api_surface_matches_reference_defaults():
+    m = PyCNN()
+    assert m.filters == O.DEFAULT_FILTERS and len(m.filters) == 19
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        m.init(batch_size=16, layers=[64, 32], learning_rate=0.01, epochs=5)
+        m.adam(beta1=0.8, beta2=0.99, eps=1e-7)
+    assert (m.batch_size, m.layers, m.learning_rate, m.epochs) == (16, [64, 32], 0.01, 5)
+    assert (m.optimizer, m.beta1, m.beta2, m.eps, m.t) == ("adam", 0.8, 0.99, 1e-7, 0)
+    assert "Network initialized with 2 hidden layers: [64, 32]" in out.getvalue()
+    assert "Adam optimizer enabled." in out.getvalue()
+    custom = [[[1, 0, -1]] * 3, [[0, 1, 0], [1, -4, 1], [0, 1, 0]]]
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.init(layers=[32], filters=custom)
+    assert m.filters == custom
+    for name in ("cuda", "adam", "init", "train_model", "predict", "save_model", "load_model",
+                 "_preprocess_image", "_forward_pass", "_backward_pass", "_gradient_decent",
+                 "_softmax_batch", "_cross_entropy_batch", "_max_pooling"):
+        assert callable(getattr(m, name))
+    assert callable(m.dataset.local) and callable(m.dataset.hf)
+
+
+def test_init_layers_uses_reference_rng_stream():
+    g = load_golden("mlp_small.npz")
+    m = PyCNN()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.init(layers=g["layers"].tolist())
+    m.dataset._init_layers(["0", "1", "2"], int(g["D"]))
+    for k in m.weights:
+        np.testing.assert_array_equal(m.weights[k], g[f"sgd_init_{k}"])
+    for k in m.biases:
+        np.testing.assert_array_equal(m.biases[k], g[f"sgd_init_{k}"])
+
+
+def test_model_bin_layout_roundtrip(tmp_path, golden_dir):
+    """model.bin written here has the reference's dict layout (pycnn/pycnn.py:693-701) and a model.bin
+    written by the reference itself loads here."""
+    m = PyCNN()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.init(layers=[6])
+        m.load_model(os.path.join(golden_dir, "ref_model.bin"))
+    assert m.classes == ["cat", "dog"] and m.layers == [6] and m.image_size == 8
+    assert m.weights["w1"].shape == (6, 18) and m.weights["w1"].dtype == np.float64
+    path = str(tmp_path / "model.bin")
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.save_model(path)
+    raw = open(path, "rb").read()
+    assert raw[:2] == b"\x80\x04"
+    ours = pickle.loads(raw)
+    ref = pickle.load(open(os.path.join(golden_dir, "ref_model.bin"), "rb"))
+    assert list(ours) == list(ref)
+    for k in ref["weights"]:
+        np.testing.assert_array_equal(ours["weights"][k], ref["weights"][k])
+        assert ours["weights"][k].dtype == np.float64
+    for k in ref["biases"]:
+        np.testing.assert_array_equal(ours["biases"][k], ref["biases"][k])
+    assert ours["filters"] == ref["filters"] and ours["classes"] == ref["classes"]
+    assert ours["layers"] == ref["layers"] and ours["image_size"] == ref["image_size"]
+
+
+def test_batch_slices_partition_every_batch():
+    for n, bs, world in [(20, 8, 2), (4096, 4096, 8), (37, 5, 4), (3, 32, 8), (65536, 4096, 3)]:
+        for start in range(0, n, bs):
+            end = min(start + bs, n)
+            got = []
+            for r in range(world):
+                lo, hi = parallel.batch_slice(start, end, r, world)
+                assert start <= lo <= hi <= end
+                got.extend(range(lo, hi))
+            assert got == list(range(start, end))
+    assert [parallel.image_shard(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+
+
+WORKER = textwrap.dedent('''
+    import os, sys
+    sys.path.insert(0, os.environ["PYCNN_ROOT"])
+    import numpy as np, torch, torch.distributed as dist
+    from oracle import pycnn_oracle as O
+    from pycnn_b200 import parallel
+    from tests.helpers import load_golden
+    rank, world, _ = parallel.init_process_group(backend="gloo")
+    assert world == 2
+    # the 128-byte id travels from rank 0 exactly as the NCCL unique id does on the GPU box
+    uid = parallel.broadcast_bytes(bytes(range(128)) if rank == 0 else None)
+    assert uid == bytes(range(128))
+    g = load_golden("mlp_small.npz")
+    layers, D, C, bs = g["layers"].tolist(), int(g["D"]), int(g["C"]), int(g["bs"])
+    data, y = g["data"], O.one_hot(g["labels"], C)
+    w, b = O.init_layers(D, layers, C, seed=42)
+    keys = list(w) + list(b)
+    def flat(gw, gb):
+        return np.concatenate([gw[k].ravel() for k in w] + [gb[k].ravel() for k in b])
+    def grad_fn(idx):
+        if len(idx) == 0:
+            return np.zeros(sum(v.size for v in list(w.values()) + list(b.values()))), 0.0, 0
+        p, acts, _ = O.forward(data[idx], w, b, layers)
+        gw, gb = O.backward(p, y[idx], acts, w, layers)
+        return flat(gw, gb), float(O.cross_entropy(p, y[idx]).sum()), int((p.argmax(1) == y[idx].argmax(1)).sum())
+    def allreduce(a):
+        t = torch.from_numpy(np.array(a, dtype=np.float64))
+        dist.all_reduce(t)                 # SUM: gradients are batch sums, no 1/world
+        return t.numpy()
+    def update_fn(gflat):
+        gw, gb, o = {}, {}, 0
+        for k in w:
+            gw[k] = gflat[o:o + w[k].size].reshape(w[k].shape); o += w[k].size
+        for k in b:
+            gb[k] = gflat[o:o + b[k].size].reshape(b[k].shape); o += b[k].size
+        O.update_cpu_rule(w, b, gw, gb, 0.05, "sgd", {}, {})
+    stepper = parallel.ShardedStepper(rank, world, grad_fn, allreduce, update_fn)
+    perms = [np.random.permutation(len(data)) for _ in range(3)]   # same stream on both ranks (seed 42)
+    totals = [stepper.epoch(p, bs) for p in perms]
+    for k in w:
+        np.testing.assert_allclose(w[k], g[f"sgd_trained_{k}"], atol=1e-12)   # == the reference's 1-process run
+    s = parallel.allreduce_scalars([1.0, float(rank)])
+    assert s == [2.0, 1.0]
+    if rank == 0:
+        print("GLOO_OK", totals[-1])
+    dist.destroy_process_group()
+''')
+
+
+def test_world2_gloo_sharded_training_equals_single_process(tmp_path):
+    """Two CPU ranks, each computing its slice of every batch with the oracle, all-reducing SUMs over
+    gloo and applying the same update: the weights equal the reference's single-process train_model."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, PYCNN_ROOT=ROOT, OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "GLOO_OK" in res.stdout
