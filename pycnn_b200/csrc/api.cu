@@ -12,7 +12,9 @@ using namespace pb;
 
 namespace {
 
-constexpr int64_t kSlackFloats = 128;  // tail slack so MN-major TMA atoms may over-read a partial atom
+constexpr int64_t kSlackFloats = 128;  // tail slack behind every fp32 buffer (vector tails, partial tiles)
+
+void drop_graphs(pycnn_b200_ctx* c);
 
 int alloc_f32(float** p, int64_t n) {
   PB_CUDA(cudaMalloc(p, sizeof(float) * (size_t)(n + kSlackFloats)));
@@ -65,6 +67,7 @@ int ensure_workspace(pycnn_b200_ctx* c, int64_t bs) {
   PB_CHECK(c->L >= 0 && c->dims.size() >= 2, "set_network must be called first");
   if (bs <= c->bs_cap) return 0;
   PB_CUDA(cudaStreamSynchronize(c->stream));
+  drop_graphs(c);
   free_workspace(c);
   const int64_t cap = round_up(bs, 128);
   PB_CUDA(cudaMalloc(&c->d_blabels, sizeof(int32_t) * cap));
@@ -84,6 +87,7 @@ int ensure_workspace(pycnn_b200_ctx* c, int64_t bs) {
 int ensure_idx(pycnn_b200_ctx* c, int64_t n) {
   if (n <= c->idx_cap) return 0;
   PB_CUDA(cudaStreamSynchronize(c->stream));
+  drop_graphs(c);
   free_dev(c->d_idx);
   c->d_idx = nullptr;
   c->idx_cap = 0;
@@ -95,6 +99,7 @@ int ensure_idx(pycnn_b200_ctx* c, int64_t n) {
 int ensure_images(pycnn_b200_ctx* c, size_t bytes, size_t n_labels) {
   if (bytes > c->images_cap) {
     PB_CUDA(cudaStreamSynchronize(c->stream));
+    drop_graphs(c);
     free_dev(c->d_images);
     c->d_images = nullptr;
     c->images_cap = 0;
@@ -105,6 +110,7 @@ int ensure_images(pycnn_b200_ctx* c, size_t bytes, size_t n_labels) {
   }
   if (n_labels > c->img_labels_cap) {
     PB_CUDA(cudaStreamSynchronize(c->stream));
+    drop_graphs(c);
     free_dev(c->d_img_labels);
     c->d_img_labels = nullptr;
     PB_CUDA(cudaMalloc(&c->d_img_labels, sizeof(int32_t) * (size_t)round_up((int64_t)n_labels, 1024)));
@@ -195,7 +201,10 @@ int backward(pycnn_b200_ctx* c, const float* x, int bs) {
       PB_TRY(gemm(c, g));
     }
     {  // db_l = sum_rows dZ_l   (backward_pass.pyx:72,93)
-      const int rows_per_block = 512;
+      // enough row chunks to fill the SMs, at least 64 rows each
+      const int col_blocks = (int)ceil_div(out_n, 32);
+      int chunks = std::max(1, std::min((int)ceil_div(bs, 64), (2 * c->num_sms + col_blocks - 1) / col_blocks));
+      const int rows_per_block = (int)ceil_div(bs, chunks);
       dim3 grid((unsigned)ceil_div(out_n, 32), (unsigned)ceil_div(bs, rows_per_block));
       float* db = c->d_grads + Bt(c, l).off;
       if (grid.y > 1) {
@@ -235,18 +244,16 @@ int apply_update(pycnn_b200_ctx* c) {
   u.lr = (float)c->lr; u.beta1 = (float)c->beta1; u.beta2 = (float)c->beta2; u.eps = (float)c->eps;
   u.eps2 = (float)(c->eps * c->eps); u.max_norm = 5.0f;
   double bc1 = 1.0, bc2 = 1.0;
-  if (c->opt == PYCNN_B200_OPT_ADAM) {
-    int64_t t;
-    if (c->update_rule == PYCNN_B200_RULE_CPU) t = 1;  // gradient_decent.pyx:58-59 with self.t never advanced
-    else t = ++c->t;
-    bc1 = 1.0 - std::pow(c->beta1, (double)t);
-    bc2 = 1.0 - std::pow(c->beta2, (double)t);
-    if (c->update_rule == PYCNN_B200_RULE_CPU) {
-      if (std::fabs(bc1) < 1e-8) bc1 = 1e-8;   // gradient_decent.pyx:64-67
-      if (std::fabs(bc2) < 1e-8) bc2 = 1e-8;
-    }
+  if (c->opt == PYCNN_B200_OPT_ADAM && c->update_rule == PYCNN_B200_RULE_CPU) {
+    // gradient_decent.pyx:58-59 with self.t never advanced by train_model: t == 1 for the whole run
+    bc1 = 1.0 - c->beta1;
+    bc2 = 1.0 - c->beta2;
+    if (std::fabs(bc1) < 1e-8) bc1 = 1e-8;   // gradient_decent.pyx:64-67
+    if (std::fabs(bc2) < 1e-8) bc2 = 1e-8;
   }
   u.inv_bc1 = (float)(1.0 / bc1); u.inv_bc2 = (float)(1.0 / bc2);
+  u.beta1_d = c->beta1; u.beta2_d = c->beta2;
+  u.steps_done = c->d_cursor;   // CuPy rule: bias corrections from the device-side step count (graph-replayable)
   if (c->update_rule == PYCNN_B200_RULE_CPU) {
     {
       LaunchScope ls(c, KC_MISC);
@@ -287,13 +294,76 @@ int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int 
   return 0;
 }
 
-int gather_batch(pycnn_b200_ctx* c, const int64_t* d_idx, int bs) {
+// rows d_idx[*cursor + extra ...] (cursor may be null: offset 0)
+int gather_batch(pycnn_b200_ctx* c, const int64_t* d_idx, const int64_t* cursor, int64_t extra, int bs) {
   if (bs == 0) return 0;
   LaunchScope ls(c, KC_GATHER);
   const int64_t total = (int64_t)bs * (c->Dp >> 2);
-  gather_rows_kernel<<<grid_for(total, 256, c->num_sms), 256, 0, c->stream>>>(c->d_feat, c->d_labels, d_idx, bs, c->Dp,
-                                                                              c->d_x, c->d_blabels);
+  gather_rows_kernel<<<grid_for(total, 256, c->num_sms), 256, 0, c->stream>>>(c->d_feat, c->d_labels, d_idx, cursor, extra, bs,
+                                                                              c->Dp, c->d_x, c->d_blabels);
   PB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int advance_cursor(pycnn_b200_ctx* c, int64_t advance) {
+  LaunchScope ls(c, KC_MISC);
+  advance_cursor_kernel<<<1, 1, 0, c->stream>>>(c->d_cursor, advance);
+  PB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+void drop_graphs(pycnn_b200_ctx* c) {
+  for (auto& kv : c->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  c->graphs.clear();
+}
+
+// Run `body` (a sequence of launches on c->stream, no host synchronisation inside) through a cached CUDA graph.
+// Falls back to eager issue when per-kernel timing is on (events inside a capture would not time anything).
+template <class Body>
+int run_graphed(pycnn_b200_ctx* c, std::tuple<int, int64_t, int64_t, int64_t, int> key, Body body) {
+  if (!c->use_graphs || c->timing) return body();
+  auto it = c->graphs.find(key);
+  if (it == c->graphs.end()) {
+    pycnn_b200_ctx::GraphEntry ent;
+    const int64_t l0 = c->launches;
+    int64_t cl0[KC_COUNT];
+    for (int k = 0; k < KC_COUNT; ++k) cl0[k] = c->class_launches[k];
+    PB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = body();
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&ent.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    ent.launches = c->launches - l0;
+    for (int k = 0; k < KC_COUNT; ++k) ent.class_launches[k] = c->class_launches[k] - cl0[k];
+    c->launches = l0;   // counted again below, per replay
+    for (int k = 0; k < KC_COUNT; ++k) c->class_launches[k] = cl0[k];
+    it = c->graphs.emplace(key, ent).first;
+  }
+  PB_CUDA(cudaGraphLaunch(it->second.exec, c->stream));
+  c->launches += it->second.launches;
+  for (int k = 0; k < KC_COUNT; ++k) c->class_launches[k] += it->second.class_launches[k];
+  return 0;
+}
+
+enum GraphKind { GK_STEP_ROWS = 1, GK_STEP_IMAGES = 2 };
+
+// one training step on dataset rows d_idx[*cursor + lo .. +bs), then cursor += advance
+int graphed_step_rows(pycnn_b200_ctx* c, int bs, int64_t lo, int64_t advance) {
+  return run_graphed(c, std::make_tuple((int)GK_STEP_ROWS, (int64_t)bs, lo, advance, 0), [&]() -> int {
+    PB_TRY(gather_batch(c, c->d_idx, c->d_cursor, lo, bs));
+    PB_TRY(step_on_batch(c, c->d_x, c->d_blabels, bs, true));
+    PB_TRY(advance_cursor(c, advance));
+    return 0;
+  });
+}
+
+int reset_cursor(pycnn_b200_ctx* c) {
+  PB_CUDA(cudaMemsetAsync(c->d_cursor, 0, sizeof(int64_t), c->stream));   // [0] only: [1] keeps counting steps
   return 0;
 }
 
@@ -407,7 +477,11 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   CREATE_CUDA(cudaMalloc(&c->d_stats, 2 * sizeof(double)));
   CREATE_CUDA(cudaMemset(c->d_stats, 0, 2 * sizeof(double)));
   CREATE_CUDA(cudaMallocHost(&c->h_stats, 2 * sizeof(double)));
+  CREATE_CUDA(cudaMalloc(&c->d_cursor, 2 * sizeof(int64_t)));
+  CREATE_CUDA(cudaMemset(c->d_cursor, 0, 2 * sizeof(int64_t)));
 #undef CREATE_CUDA
+  { const char* g = getenv("PYCNN_B200_GRAPHS"); if (g && g[0] == '0') c->use_graphs = false; }
+  if (tc_gemm_prepare(c) != 0 || tc_extract_prepare(c) != 0) return bail(1);
   if (resolve_encode_tiled(c) != 0) return bail(1);
   *out = c;
   return 0;
@@ -417,7 +491,9 @@ int pycnn_b200_destroy(pycnn_b200_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  drop_graphs(c);
   pycnn_b200_comm_destroy(c);
+  free_dev(c->d_cursor);
   free_network(c);
   free_dataset(c);
   free_dev(c->d_taps); free_dev(c->d_tc_filters); free_dev(c->d_tc_scale);
@@ -446,18 +522,21 @@ int pycnn_b200_synchronize(pycnn_b200_ctx* c) {
 int pycnn_b200_set_math_mode(pycnn_b200_ctx* c, int mode) {
   CTX_GUARD(c);
   PB_CHECK(mode == PYCNN_B200_MATH_FP32_SIMT || mode == PYCNN_B200_MATH_TF32, "unknown math mode %d", mode);
+  drop_graphs(c);
   c->math_mode = mode;
   return 0;
 }
 int pycnn_b200_set_update_rule(pycnn_b200_ctx* c, int rule) {
   CTX_GUARD(c);
   PB_CHECK(rule == PYCNN_B200_RULE_CPU || rule == PYCNN_B200_RULE_CUPY, "unknown update rule %d", rule);
+  drop_graphs(c);
   c->update_rule = rule;
   return 0;
 }
 int pycnn_b200_set_extract_mode(pycnn_b200_ctx* c, int mode) {
   CTX_GUARD(c);
   PB_CHECK(mode == PYCNN_B200_EXTRACT_SIMT || mode == PYCNN_B200_EXTRACT_TC, "unknown extract mode %d", mode);
+  drop_graphs(c);
   c->extract_mode = mode;
   return 0;
 }
@@ -477,6 +556,7 @@ int pycnn_b200_set_filters(pycnn_b200_ctx* c, const double* taps, int F) {
   CTX_GUARD(c);
   PB_CHECK(taps && F > 0, "set_filters needs at least one 3x3 filter");
   PB_CUDA(cudaStreamSynchronize(c->stream));
+  drop_graphs(c);
   c->h_taps.assign(taps, taps + (size_t)F * 9);
   std::vector<float> flipped((size_t)F * 9);
   for (int f = 0; f < F; ++f)
@@ -501,6 +581,8 @@ int pycnn_b200_feature_count(pycnn_b200_ctx* c, int image_size, int64_t* out) {
 static int extract_host(pycnn_b200_ctx* c, const uint8_t* images, int64_t n, int S, double* out64, float* out32) {
   CTX_GUARD(c);
   PB_CHECK(n >= 0 && (n == 0 || images), "null images");
+  PB_CHECK(c->F > 0, "set_filters must be called before extraction");
+  PB_CHECK(S >= 4, "image_size must be >= 4 (got %d)", S);
   if (n == 0) return 0;
   const int64_t D = feature_count(c, S);
   const int64_t ld = round_up(D, 4);
@@ -601,6 +683,7 @@ int pycnn_b200_set_network(pycnn_b200_ctx* c, int64_t D, const int* layers, int 
   PB_CHECK(D > 0 && L >= 0 && C > 0 && (L == 0 || layers), "bad network shape");
   for (int l = 0; l < L; ++l) PB_CHECK(layers[l] > 0, "layer %d has size %d", l, layers[l]);
   PB_CUDA(cudaStreamSynchronize(c->stream));
+  drop_graphs(c);
   if (c->D != D) free_dataset(c);
   free_network(c);
   c->D = D; c->Dp = round_up(D, 4); c->L = L; c->C = C;
@@ -674,7 +757,9 @@ int pycnn_b200_set_opt_state(pycnn_b200_ctx* c, int which, int index, const doub
 int pycnn_b200_set_optimizer(pycnn_b200_ctx* c, int kind, double lr, double beta1, double beta2, double eps) {
   CTX_GUARD(c);
   PB_CHECK(kind == PYCNN_B200_OPT_SGD || kind == PYCNN_B200_OPT_ADAM, "unknown optimizer %d", kind);
+  drop_graphs(c);   // lr / betas are baked into the captured update kernel
   c->opt = kind; c->lr = lr; c->beta1 = beta1; c->beta2 = beta2; c->eps = eps; c->t = 0;
+  PB_CUDA(cudaMemsetAsync(c->d_cursor, 0, 2 * sizeof(int64_t), c->stream));
   if (c->d_m) {
     PB_CUDA(cudaMemsetAsync(c->d_m, 0, sizeof(float) * c->P, c->stream));
     PB_CUDA(cudaMemsetAsync(c->d_v, 0, sizeof(float) * c->P, c->stream));
@@ -694,6 +779,7 @@ int pycnn_b200_dataset_alloc(pycnn_b200_ctx* c, int64_t rows) {
   PB_CHECK(c->D > 0, "set_network must be called first");
   PB_CHECK(rows > 0, "dataset needs at least one row");
   PB_CUDA(cudaStreamSynchronize(c->stream));
+  drop_graphs(c);
   free_dataset(c);
   PB_TRY(alloc_f32(&c->d_feat, rows * c->Dp));
   PB_CUDA(cudaMalloc(&c->d_labels, sizeof(int32_t) * rows));
@@ -782,8 +868,9 @@ int pycnn_b200_train_step(pycnn_b200_ctx* c, const int64_t* idx, int bs, double*
   PB_TRY(ensure_idx(c, bs));
   PB_CUDA(cudaMemcpyAsync(c->d_idx, idx, sizeof(int64_t) * bs, cudaMemcpyHostToDevice, c->stream));
   PB_TRY(zero_stats(c));
-  PB_TRY(gather_batch(c, c->d_idx, bs));
-  PB_TRY(step_on_batch(c, c->d_x, c->d_blabels, bs, true));
+  PB_TRY(reset_cursor(c));
+  PB_TRY(graphed_step_rows(c, bs, 0, bs));
+  if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += 1;
   if (loss_sum || correct) PB_TRY(read_stats(c, loss_sum, correct, true));
   return 0;
 }
@@ -797,10 +884,9 @@ int pycnn_b200_train_steps(pycnn_b200_ctx* c, const int64_t* idx, int bs, int st
   PB_TRY(ensure_idx(c, (int64_t)bs * steps));
   PB_CUDA(cudaMemcpyAsync(c->d_idx, idx, sizeof(int64_t) * bs * steps, cudaMemcpyHostToDevice, c->stream));
   PB_TRY(zero_stats(c));
-  for (int s = 0; s < steps; ++s) {
-    PB_TRY(gather_batch(c, c->d_idx + (int64_t)s * bs, bs));
-    PB_TRY(step_on_batch(c, c->d_x, c->d_blabels, bs, true));
-  }
+  PB_TRY(reset_cursor(c));
+  for (int s = 0; s < steps; ++s) PB_TRY(graphed_step_rows(c, bs, 0, bs));
+  if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += steps;
   if (loss_sum || correct) PB_TRY(read_stats(c, loss_sum, correct, true));
   return 0;
 }
@@ -817,13 +903,14 @@ int pycnn_b200_train_epoch(pycnn_b200_ctx* c, const int64_t* perm, int64_t n, in
   PB_TRY(ensure_idx(c, n));
   PB_CUDA(cudaMemcpyAsync(c->d_idx, perm, sizeof(int64_t) * n, cudaMemcpyHostToDevice, c->stream));
   PB_TRY(zero_stats(c));
+  PB_TRY(reset_cursor(c));
   for (int64_t start = 0; start < n; start += batch_size) {   // pycnn/pycnn.py:626-627
     const int64_t end = std::min<int64_t>(start + batch_size, n);
     const int64_t len = end - start, per = ceil_div(len, W);
     const int64_t lo = std::min(len, per * R), hi = std::min(len, per * (R + 1));
     const int bs = (int)(hi - lo);
-    PB_TRY(gather_batch(c, c->d_idx + start + lo, bs));
-    PB_TRY(step_on_batch(c, c->d_x, c->d_blabels, bs, true));
+    PB_TRY(graphed_step_rows(c, bs, lo, len));   // one graph per distinct (local bs, offset, batch length)
+    if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += 1;
   }
   PB_TRY(read_stats(c, loss_sum, correct, true));
   return 0;
@@ -841,8 +928,13 @@ int pycnn_b200_train_step_images(pycnn_b200_ctx* c, const uint8_t* images, const
   PB_CUDA(cudaMemcpyAsync(c->d_images, images, img_bytes, cudaMemcpyHostToDevice, c->stream));
   PB_CUDA(cudaMemcpyAsync(c->d_blabels, labels, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
   PB_TRY(zero_stats(c));
-  PB_TRY(extract_device(c, c->d_images, n, S, c->d_x, c->Dp));
-  PB_TRY(step_on_batch(c, c->d_x, c->d_blabels, n, true));
+  PB_TRY(run_graphed(c, std::make_tuple((int)GK_STEP_IMAGES, (int64_t)n, (int64_t)S, (int64_t)0, 0), [&]() -> int {
+    PB_TRY(extract_device(c, c->d_images, n, S, c->d_x, c->Dp));
+    PB_TRY(step_on_batch(c, c->d_x, c->d_blabels, n, true));
+    PB_TRY(advance_cursor(c, 0));
+    return 0;
+  }));
+  if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += 1;
   if (loss_sum || correct) PB_TRY(read_stats(c, loss_sum, correct, true));
   return 0;
 }
@@ -856,7 +948,7 @@ int pycnn_b200_forward_backward(pycnn_b200_ctx* c, const int64_t* idx, int bs) {
     PB_TRY(ensure_workspace(c, bs));
     PB_TRY(ensure_idx(c, bs));
     PB_CUDA(cudaMemcpyAsync(c->d_idx, idx, sizeof(int64_t) * bs, cudaMemcpyHostToDevice, c->stream));
-    PB_TRY(gather_batch(c, c->d_idx, bs));
+    PB_TRY(gather_batch(c, c->d_idx, nullptr, 0, bs));
   }
   PB_TRY(step_on_batch(c, c->d_x, c->d_blabels, bs, false));
   PB_CUDA(cudaStreamSynchronize(c->stream));  // the external all-reduce runs on someone else's stream
@@ -866,7 +958,10 @@ int pycnn_b200_forward_backward(pycnn_b200_ctx* c, const int64_t* idx, int bs) {
 int pycnn_b200_apply_update(pycnn_b200_ctx* c) {
   CTX_GUARD(c);
   PB_CHECK(c->d_params, "set_network must be called first");
-  return apply_update(c);
+  PB_TRY(apply_update(c));
+  PB_TRY(advance_cursor(c, 0));
+  if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += 1;
+  return 0;
 }
 
 int pycnn_b200_read_step_stats(pycnn_b200_ctx* c, double* loss_sum, int64_t* correct, int reset) {
@@ -892,7 +987,7 @@ int pycnn_b200_forward_rows(pycnn_b200_ctx* c, const int64_t* idx, int64_t row0,
     PB_TRY(check_idx_host(c, idx, bs));
     PB_TRY(ensure_idx(c, bs));
     PB_CUDA(cudaMemcpyAsync(c->d_idx, idx, sizeof(int64_t) * bs, cudaMemcpyHostToDevice, c->stream));
-    PB_TRY(gather_batch(c, c->d_idx, bs));
+    PB_TRY(gather_batch(c, c->d_idx, nullptr, 0, bs));
     x = c->d_x;
   } else {
     PB_CHECK(row0 >= 0 && row0 + bs <= c->n_rows, "rows [%lld,%lld) outside the dataset", (long long)row0, (long long)(row0 + bs));
@@ -1027,6 +1122,7 @@ int pycnn_b200_comm_init(pycnn_b200_ctx* c, const char* id128, int rank, int wor
   NcclApi* api = nccl_api();
   PB_CHECK(api, "could not load libnccl.so.2 (set PYCNN_B200_NCCL_LIB)");
   PB_TRY(pycnn_b200_comm_destroy(c));
+  drop_graphs(c);
   NcclUniqueId id;
   memcpy(id.internal, id128, 128);
   NcclComm comm = nullptr;
@@ -1040,6 +1136,8 @@ int pycnn_b200_comm_init(pycnn_b200_ctx* c, const char* id128, int rank, int wor
 int pycnn_b200_comm_destroy(pycnn_b200_ctx* c) {
   PB_CHECK(c, "null context");
   if (c->nccl_comm) {
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    drop_graphs(c);
     NcclApi* api = nccl_api();
     if (api) api->CommDestroy(c->nccl_comm);
     c->nccl_comm = nullptr;
@@ -1076,7 +1174,7 @@ int pycnn_b200_event_elapsed_ms(pycnn_b200_ctx* c, int a, int b, float* ms) {
 int pycnn_b200_set_kernel_timing(pycnn_b200_ctx* c, int enabled) {
   CTX_GUARD(c);
   PB_CUDA(cudaStreamSynchronize(c->stream));
-  c->timing = enabled != 0;
+  c->timing = enabled != 0;   // while on, steps are issued eagerly (not through graphs) so each launch can be timed
   return 0;
 }
 

@@ -9,7 +9,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/pycnn_b200.h"
@@ -182,6 +184,16 @@ struct pycnn_b200_ctx {
 
   // TMA descriptor encoder (driver entry point resolved at create time)
   void* encode_tiled = nullptr;
+
+  // CUDA-graph replay of the training step (the step is ~30 short launches: launch-bound when issued eagerly)
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+    int64_t class_launches[pb::KC_COUNT] = {};
+  };
+  std::map<std::tuple<int, int64_t, int64_t, int64_t, int>, GraphEntry> graphs;
+  bool use_graphs = true;
+  int64_t* d_cursor = nullptr;   // [0] offset into d_idx of the current batch, [1] completed steps (device-side t)
 };
 
 namespace pb {

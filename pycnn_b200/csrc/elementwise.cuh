@@ -39,10 +39,15 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
 // K8: batch_x = data[batch_idx], batch_y = labels[batch_idx]   (pycnn/pycnn.py:629-630)
 // rows are Dp floats (Dp % 4 == 0, 16-byte aligned): one float4 per thread, grid-strided.
 // ---------------------------------------------------------------------------------------------
+// The batch's indices are idx_base[*cursor + extra ...]: the cursor lives on the device so that one captured
+// CUDA graph can be replayed for every batch of an epoch (advance_cursor_kernel moves it).
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ feat,
                                                           const int32_t* __restrict__ labels,
-                                                          const int64_t* __restrict__ idx, int bs, int64_t Dp,
-                                                          float* __restrict__ x, int32_t* __restrict__ blabels) {
+                                                          const int64_t* __restrict__ idx_base,
+                                                          const int64_t* __restrict__ cursor, int64_t extra, int bs,
+                                                          int64_t Dp, float* __restrict__ x,
+                                                          int32_t* __restrict__ blabels) {
+  const int64_t* __restrict__ idx = idx_base + (cursor ? cursor[0] : 0) + extra;
   const int64_t vec_per_row = Dp >> 2;
   const int64_t total = (int64_t)bs * vec_per_row;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -126,25 +131,27 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
 
 // ---------------------------------------------------------------------------------------------
 // K6(c): db[n] = sum_rows dZ[m, n]  (backward_pass.pyx:72,93).  dz [bs, ld].  grid (ceil(N/32), R);
-// block (32, 8).  db must be zeroed when R > 1 (atomics); with R == 1 plain stores.
+// block (32, 8): thread (x, y) sums rows y, y+8, ... of its row chunk for column x in FP64, the 8 partials
+// are combined through smem and one atomicAdd per (column, chunk) lands in db (zeroed by the caller
+// when R > 1).  Coalesced 128-byte row segments; R is chosen so the grid fills the SMs.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dz, int bs, int N, int64_t ld,
                                                      float* __restrict__ db, int rows_per_block) {
-  __shared__ float red[8][33];
+  __shared__ double red[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(bs, r0 + rows_per_block);
-  float acc = 0.f;
+  double acc = 0.0;
   if (n < N)
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += dz[(int64_t)r * ld + n];
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += (double)dz[(int64_t)r * ld + n];
   red[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && n < N) {
-    float s = 0.f;
+    double s = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-    if (gridDim.y == 1) db[n] = s;
-    else atomicAdd(&db[n], s);
+    if (gridDim.y == 1) db[n] = (float)s;
+    else atomicAdd(&db[n], (float)s);
   }
 }
 
@@ -181,7 +188,14 @@ struct UpdateParams {
   int opt;       // 0 sgd, 1 adam
   int rule;      // 0 cpu (clip + skip), 1 cupy
   float lr, beta1, beta2, eps, inv_bc1, inv_bc2, eps2, max_norm;
+  double beta1_d, beta2_d;
+  const int64_t* steps_done;  // device-side count of completed updates (CuPy rule: t = steps_done + 1)
 };
+
+__global__ void advance_cursor_kernel(int64_t* cursor, int64_t advance) {
+  cursor[0] += advance;
+  cursor[1] += 1;
+}
 
 // clipped SGD / Adam over the flat buffers; each block handles one chunk and reads its tensor's norm.
 // CPU rule (gradient_decent.pyx): g *= 5/||g|| when ||g|| > 5 (:33-35); non-finite -> skip tensor
@@ -193,6 +207,11 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ pa
                                                           const double* __restrict__ norm2, UpdateParams u) {
   const Chunk ch = chunks[blockIdx.x];
   float scale = 1.0f;
+  if (u.rule == 1 && u.opt == 1) {   // pycnn/pycnn.py:534,544-545: t advances, 1 - beta^t
+    const double t = (double)(u.steps_done[1] + 1);
+    u.inv_bc1 = (float)(1.0 / (1.0 - pow(u.beta1_d, t)));
+    u.inv_bc2 = (float)(1.0 / (1.0 - pow(u.beta2_d, t)));
+  }
   if (u.rule == 0) {
     const double n2 = norm2[ch.tensor];
     if (!isfinite(n2)) return;  // NaN/Inf gradient: skip this tensor's update

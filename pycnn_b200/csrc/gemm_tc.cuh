@@ -15,8 +15,10 @@
 //   warps 2-5          epilogue: tcgen05.ld (32 lanes x 32 cols) -> bias / ReLU / ReLU-mask ->
 //                      128-bit global stores, or red.global.add.v4.f32 for split-K partials
 // K-major tiles are [rows][32 floats] with SWIZZLE_128B (SBO 1024 B); MN-major tiles are
-// [MN/32 atoms][32 k-rows][32 floats] (LBO = 4096 B between atoms, SBO = 1024 B between 8-row
-// groups), loaded by ONE 3-D TMA box per operand (dims {32, K, MN/32}, strides {pitch, 128 B}).
+// [MN/32 atoms][32 k-rows][32 floats] in the SWIZZLE_128B_BASE32B form -- the only smem layout the
+// tensor core accepts for MN-major TF32 (32-B swizzle granules, 4 k-rows per atom; LBO = 4096 B between
+// MN atoms, SBO = 512 B between 4-row groups) -- loaded by one {32 x 32} TMA box per atom from a plain
+// 2-D map {MN, K} encoded with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
 #pragma once
 #include "elementwise.cuh"
 #include "tc_common.cuh"
@@ -48,6 +50,7 @@ struct TcGemmArgs {
   const float* bias;
   const float* mask;
   int64_t ldmask;
+  int mn_variant;    // debug: 1 swaps LBO/SBO of the MN-major descriptors (PYCNN_B200_MN_VARIANT)
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -100,10 +103,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint8_t* sb = sa + Cfg::A_BYTES;
         mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         const int k0 = (kb0 + i) * G_BK;
-        if (A_MN) tma_load_3d(sa, &map_a, &full_bar[s], 0, k0, m0 / 32);
-        else      tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);
-        if (B_MN) tma_load_3d(sb, &map_b, &full_bar[s], 0, k0, n0 / 32);
-        else      tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);
+        if (A_MN) {
+#pragma unroll
+          for (int at = 0; at < G_BM / 32; ++at) tma_load_2d(sa + at * (G_BK * 128), &map_a, &full_bar[s], m0 + at * 32, k0);
+        } else {
+          tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int at = 0; at < BN / 32; ++at) tma_load_2d(sb + at * (G_BK * 128), &map_b, &full_bar[s], n0 + at * 32, k0);
+        } else {
+          tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -120,9 +131,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
         for (int k = 0; k < G_BK / 8; ++k) {
           // K-major: advance 8 floats (32 B) inside the 128-B swizzle row; MN-major: next 8 k-rows (1024 B)
-          const uint64_t da = A_MN ? make_smem_desc(sa + k * 1024, G_BK * 128, 1024, UMMA_SWIZZLE_128B)
+          // MN-major TF32 operands only exist in the SWIZZLE_128B_BASE32B form (32-byte swizzle granules,
+          // 4 k-rows per 512-B atom): LBO = stride between 32-float MN atoms, SBO = stride between 4-row groups
+          const uint32_t mn_lbo = g.mn_variant ? 512u : (uint32_t)(G_BK * 128);
+          const uint32_t mn_sbo = g.mn_variant ? (uint32_t)(G_BK * 128) : 512u;
+          const uint64_t da = A_MN ? make_smem_desc(sa + k * 1024, mn_lbo, mn_sbo, UMMA_SWIZZLE_128B_BASE32B)
                                    : make_smem_desc(sa + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
-          const uint64_t db = B_MN ? make_smem_desc(sb + k * 1024, G_BK * 128, 1024, UMMA_SWIZZLE_128B)
+          const uint64_t db = B_MN ? make_smem_desc(sb + k * 1024, mn_lbo, mn_sbo, UMMA_SWIZZLE_128B_BASE32B)
                                    : make_smem_desc(sb + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
           mma_tf32(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
@@ -222,19 +237,19 @@ static inline int make_map_kmajor(pycnn_b200_ctx* c, CUtensorMap* map, const flo
   return 0;
 }
 
-// MN-major operand: matrix [K, MN] row-major with pitch ld.  Viewed as 3-D {32, K, ceil(MN/32)} with
-// strides {ld*4, 128} bytes so one box {32, 32, box_atoms} lands as [atom][k][32 floats] in smem.
+// MN-major operand: matrix [K, MN] row-major with pitch ld.  Plain 2-D map {MN (inner), K}; the kernel issues
+// one {32 floats, 32 k-rows} box per 32-wide MN atom so smem holds [atom][k][32 floats] (128-B swizzled rows).
 static inline int make_map_mnmajor(pycnn_b200_ctx* c, CUtensorMap* map, const float* base, int64_t K, int64_t MN,
-                                   int64_t ld, int box_atoms) {
+                                   int64_t ld) {
   PB_TRY(resolve_encode_tiled(c));
   PB_CHECK((ld & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand needs 16-byte aligned rows (ld=%lld)", (long long)ld);
-  cuuint64_t dims[3] = {32, (cuuint64_t)K, (cuuint64_t)ceil_div(MN, 32)};
-  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
-  cuuint32_t box[3] = {32, 32, (cuuint32_t)box_atoms};
-  cuuint32_t es[3] = {1, 1, 1};
+  cuuint64_t dims[2] = {(cuuint64_t)MN, (cuuint64_t)K};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t es[2] = {1, 1};
   CUresult r = reinterpret_cast<EncodeTiledFn>(c->encode_tiled)(
-      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
-      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(MN-major K=%lld MN=%lld ld=%lld) failed: %d", (long long)K, (long long)MN, (long long)ld, (int)r);
   return 0;
@@ -252,15 +267,32 @@ struct GemmCall {
 };
 
 template <int BN, bool A_MN, bool B_MN>
+static int prepare_tc_gemm() {
+  PB_CUDA(cudaFuncSetAttribute(tc::gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               tc::GemmCfg<BN>::SMEM_BYTES));
+  return 0;
+}
+template <bool A_MN, bool B_MN>
+static int prepare_tc_gemm_bn() {
+  PB_TRY((prepare_tc_gemm<32, A_MN, B_MN>()));
+  PB_TRY((prepare_tc_gemm<64, A_MN, B_MN>()));
+  PB_TRY((prepare_tc_gemm<128, A_MN, B_MN>()));
+  PB_TRY((prepare_tc_gemm<256, A_MN, B_MN>()));
+  return 0;
+}
+// opt every instantiation into > 48 KB of dynamic smem once per device, outside any stream capture
+static int tc_gemm_prepare(pycnn_b200_ctx*) {
+  PB_TRY((prepare_tc_gemm_bn<false, false>()));
+  PB_TRY((prepare_tc_gemm_bn<false, true>()));
+  PB_TRY((prepare_tc_gemm_bn<true, true>()));
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
 static int launch_tc_gemm(pycnn_b200_ctx* c, const GemmCall& g, const CUtensorMap& ma, const CUtensorMap& mb,
                           const tc::TcGemmArgs& args, dim3 grid) {
   using Cfg = tc::GemmCfg<BN>;
-  static bool attr_set[16] = {};
   auto kern = tc::gemm_tf32_kernel<BN, A_MN, B_MN>;
-  if (!attr_set[c->device & 15]) {
-    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set[c->device & 15] = true;
-  }
   kern<<<grid, 192, Cfg::SMEM_BYTES, c->stream>>>(ma, mb, args);
   PB_CUDA(cudaGetLastError());
   return 0;
@@ -294,14 +326,15 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   split = (int)ceil_div(num_kb, kb_per_split);  // no empty slices
   CUtensorMap ma, mb;
   if (g.a_kmajor) PB_TRY(make_map_kmajor(c, &ma, g.A, g.M, g.K, g.lda, tc::G_BM));
-  else            PB_TRY(make_map_mnmajor(c, &ma, g.A, g.K, g.M, g.lda, tc::G_BM / 32));
+  else            PB_TRY(make_map_mnmajor(c, &ma, g.A, g.K, g.M, g.lda));
   if (g.b_kmajor) PB_TRY(make_map_kmajor(c, &mb, g.B, g.N, g.K, g.ldb, BN));
-  else            PB_TRY(make_map_mnmajor(c, &mb, g.B, g.K, g.N, g.ldb, BN / 32));
+  else            PB_TRY(make_map_mnmajor(c, &mb, g.B, g.K, g.N, g.ldb));
   tc::TcGemmArgs a;
   a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.N = g.N; a.K = g.K;
   a.epi = g.epi; a.atomic = split > 1 ? 1 : 0;
   a.num_kb = num_kb; a.kb_per_split = kb_per_split;
   a.bias = g.bias; a.mask = g.mask; a.ldmask = g.ldmask;
+  { const char* v = getenv("PYCNN_B200_MN_VARIANT"); a.mn_variant = (v && v[0] == '1') ? 1 : 0; }
   dim3 grid(tiles_n, tiles_m, split);
   if (split > 1) {
     LaunchScope ls(c, KC_MISC);

@@ -78,7 +78,9 @@ __global__ void __launch_bounds__(256) extract_simt_kernel(const uint8_t* __rest
 //   epi 1: C = acc + bias   (output logits, forward_pass.pyx:36-37)
 //   epi 2: C = relu(acc+b)  (hidden layers, forward_pass.pyx:29-32)
 //   epi 3: C = acc where mask>0 else 0   (dA then ReLU mask, backward_pass.pyx:85-86,97)
-// 64x64 tile, BK 16, 256 threads, 4x4 register micro-tile.
+// 64x64 tile, BK 16, 256 threads, 4x4 register micro-tile.  Operands are FP32, products and sums are
+// FP64 (DFMA): as the *verification* mode its job is to remove accumulation-order noise so that what is
+// left against the float64 reference is only the FP32 storage of weights/activations.
 // ---------------------------------------------------------------------------------------------
 struct SimtGemmArgs {
   const float* A; int64_t sam, sak;
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(256) sgemm_simt_kernel(SimtGemmArgs g) {
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  float acc[4][4] = {};
+  double acc[4][4] = {};
   const bool a_kfast = (g.sak == 1), b_kfast = (g.sbk == 1);
   for (int k0 = 0; k0 < g.K; k0 += BK) {
 #pragma unroll
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(256) sgemm_simt_kernel(SimtGemmArgs g) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma((double)a[i], (double)b[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -133,8 +135,7 @@ __global__ void __launch_bounds__(256) sgemm_simt_kernel(SimtGemmArgs g) {
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= g.N) continue;
-      float v = acc[i][j];
-      if (g.epi == 1 || g.epi == 2) v += g.bias[n];
+      float v = (g.epi == 1 || g.epi == 2) ? (float)(acc[i][j] + (double)g.bias[n]) : (float)acc[i][j];
       if (g.epi == 2) v = (v < 0.f) ? 0.f : v;   // relu_inplace: NaN stays NaN (forward_pass.pyx:12)
       if (g.epi == 3) v = (g.mask[(int64_t)m * g.ldmask + n] <= 0.f) ? 0.f : v;   // dz[z<=0]=0 (backward_pass.pyx:86)
       g.C[(int64_t)m * g.ldc + n] = v;

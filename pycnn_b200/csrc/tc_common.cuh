@@ -161,7 +161,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 // shared-memory matrix descriptor, SWIZZLE_128B, Blackwell version bit set
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4
 //   bits [32,46) stride byte offset >> 4   bits [46,48) version = 1      bits [61,64) layout type
-enum : uint32_t { UMMA_SWIZZLE_NONE = 0, UMMA_SWIZZLE_128B = 2, UMMA_SWIZZLE_64B = 4, UMMA_SWIZZLE_32B = 6 };
+enum : uint32_t { UMMA_SWIZZLE_NONE = 0, UMMA_SWIZZLE_128B_BASE32B = 1, UMMA_SWIZZLE_128B = 2, UMMA_SWIZZLE_64B = 4, UMMA_SWIZZLE_32B = 6 };
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t layout) {
   uint64_t d = 0;
