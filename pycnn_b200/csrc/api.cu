@@ -42,9 +42,20 @@ int gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   a.M = g.M; a.N = g.N; a.K = g.K; a.epi = g.epi;
   a.bias = g.bias; a.mask = g.mask; a.ldmask = g.ldmask;
   dim3 grid((unsigned)ceil_div(g.N, 64), (unsigned)ceil_div(g.M, 64));
-  LaunchScope ls(c, g.cls);
-  sgemm_simt_kernel<<<grid, 256, 0, c->stream>>>(a);
-  PB_CUDA(cudaGetLastError());
+  {
+    LaunchScope ls(c, g.cls);
+    sgemm_simt_kernel<<<grid, 256, 0, c->stream>>>(a);
+    PB_CUDA(cudaGetLastError());
+  }
+  if (g.colsum) {   // the tensor-core kernel fuses this into its epilogue
+    const int col_blocks = (int)ceil_div(g.N, 32);
+    const int chunks = std::max(1, std::min((int)ceil_div(g.M, 64), (2 * c->num_sms + col_blocks - 1) / col_blocks));
+    const int rows_per_block = (int)ceil_div(g.M, chunks);
+    dim3 cgrid((unsigned)col_blocks, (unsigned)ceil_div(g.M, rows_per_block));
+    LaunchScope ls(c, KC_COLSUM);
+    colsum_kernel<<<cgrid, dim3(32, 8), 0, c->stream>>>(g.C, g.M, g.N, g.ldc, g.colsum, rows_per_block, 1);
+    PB_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -175,16 +186,34 @@ int forward_logits(pycnn_b200_ctx* c, const float* x, int bs) {
   return 0;
 }
 
+// logits live in c->d_probs.  train: writes dZ, accumulates loss/#correct and db_o, does the step bookkeeping.
 int softmax_ce(pycnn_b200_ctx* c, int bs, const int32_t* labels, bool write_probs, bool write_dz, bool write_pred,
-               bool stats) {
+               bool stats, bool train = false, int64_t advance = 0) {
   LaunchScope ls(c, KC_SOFTMAX_CE);
   const int blocks = (int)ceil_div(bs, 8);
-  softmax_ce_kernel<<<blocks, 256, 0, c->stream>>>(c->d_probs, bs, c->C, c->ldw[c->L + 1], labels,
-                                                   write_probs ? c->d_probs : nullptr,
-                                                   write_dz ? c->d_dz[c->L] : nullptr,
-                                                   write_pred ? c->d_pred : nullptr, write_pred ? c->d_conf : nullptr,
-                                                   stats ? c->d_stats : nullptr);
+  StepBookkeeping bk{nullptr, 0, nullptr, 0};
+  float* db = nullptr;
+  size_t smem = 0;
+  if (train) {
+    bk.norm2 = c->d_norm2; bk.n_norm = (int)c->tensors.size();
+    bk.cursor = c->d_cursor; bk.advance = advance;
+    db = c->d_grads + c->tensors[2 * c->L + 1].off;
+    smem = sizeof(float) * (size_t)c->C;
+  }
+  softmax_ce_kernel<<<blocks, 256, smem, c->stream>>>(c->d_probs, bs, c->C, c->ldw[c->L + 1], labels,
+                                                      write_probs ? c->d_probs : nullptr,
+                                                      write_dz ? c->d_dz[c->L] : nullptr,
+                                                      write_pred ? c->d_pred : nullptr, write_pred ? c->d_conf : nullptr,
+                                                      stats ? c->d_stats : nullptr, db, bk);
   PB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Gradient buffers are zeroed once per step (zero_grads): split-K dW partial sums and the fused bias-gradient
+// column sums (softmax kernel for the output layer, dA-GEMM epilogue for hidden layers) accumulate into them.
+int zero_grads(pycnn_b200_ctx* c) {
+  LaunchScope ls(c, KC_MISC);
+  PB_CUDA(cudaMemsetAsync(c->d_grads, 0, sizeof(float) * c->P, c->stream));
   return 0;
 }
 
@@ -198,30 +227,17 @@ int backward(pycnn_b200_ctx* c, const float* x, int bs) {
       g.B = in; g.ldb = c->ldw[l]; g.b_kmajor = false;
       g.C = c->d_grads + Wt(c, l).off; g.ldc = Wt(c, l).ld;
       g.M = out_n; g.N = in_n; g.K = bs; g.epi = 0; g.cls = KC_GEMM_DW;
+      g.c_is_zero = true;
       PB_TRY(gemm(c, g));
     }
-    {  // db_l = sum_rows dZ_l   (backward_pass.pyx:72,93)
-      // enough row chunks to fill the SMs, at least 64 rows each
-      const int col_blocks = (int)ceil_div(out_n, 32);
-      int chunks = std::max(1, std::min((int)ceil_div(bs, 64), (2 * c->num_sms + col_blocks - 1) / col_blocks));
-      const int rows_per_block = (int)ceil_div(bs, chunks);
-      dim3 grid((unsigned)ceil_div(out_n, 32), (unsigned)ceil_div(bs, rows_per_block));
-      float* db = c->d_grads + Bt(c, l).off;
-      if (grid.y > 1) {
-        LaunchScope ls(c, KC_MISC);
-        PB_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * out_n, c->stream));
-      }
-      LaunchScope ls(c, KC_COLSUM);
-      colsum_kernel<<<grid, dim3(32, 8), 0, c->stream>>>(c->d_dz[l], bs, out_n, c->ldw[l + 1], db, rows_per_block);
-      PB_CUDA(cudaGetLastError());
-    }
-    if (l > 0) {  // dZ_{l-1} = (dZ_l . W_l) masked by act_{l-1} > 0   (backward_pass.pyx:85-86,97)
+    if (l > 0) {  // dZ_{l-1} = (dZ_l . W_l) masked by act_{l-1} > 0 (backward_pass.pyx:85-86,97); db_{l-1} = colsum (:93)
       GemmCall g{};
       g.A = c->d_dz[l]; g.lda = c->ldw[l + 1]; g.a_kmajor = true;
       g.B = c->d_params + Wt(c, l).off; g.ldb = Wt(c, l).ld; g.b_kmajor = false;
       g.C = c->d_dz[l - 1]; g.ldc = c->ldw[l];
       g.M = bs; g.N = in_n; g.K = out_n; g.epi = 3;
       g.mask = c->d_act[l - 1]; g.ldmask = c->ldw[l];
+      g.colsum = c->d_grads + Bt(c, l - 1).off;
       g.cls = KC_GEMM_DA;
       PB_TRY(gemm(c, g));
     }
@@ -254,11 +270,7 @@ int apply_update(pycnn_b200_ctx* c) {
   u.inv_bc1 = (float)(1.0 / bc1); u.inv_bc2 = (float)(1.0 / bc2);
   u.beta1_d = c->beta1; u.beta2_d = c->beta2;
   u.steps_done = c->d_cursor;   // CuPy rule: bias corrections from the device-side step count (graph-replayable)
-  if (c->update_rule == PYCNN_B200_RULE_CPU) {
-    {
-      LaunchScope ls(c, KC_MISC);
-      PB_CUDA(cudaMemsetAsync(c->d_norm2, 0, sizeof(double) * c->tensors.size(), c->stream));
-    }
+  if (c->update_rule == PYCNN_B200_RULE_CPU) {   // d_norm2 was zeroed by this step's softmax kernel
     LaunchScope ls(c, KC_SQNORM);
     grad_sqnorm_kernel<<<c->num_chunks, 256, 0, c->stream>>>(c->d_grads, c->d_chunks, c->d_norm2);
     PB_CUDA(cudaGetLastError());
@@ -271,21 +283,19 @@ int apply_update(pycnn_b200_ctx* c) {
 }
 
 // full step on x [bs, Dp] + labels (device).  bs may be 0 on a rank whose slice is empty.
-int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int bs, bool update) {
+int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int bs, bool update, int64_t advance = 0) {
   if (bs > 0) {
     PB_TRY(forward_logits(c, x, bs));
-    // aliasing note: probs are not written during training; dZ goes to its own buffer
-    {
-      LaunchScope ls(c, KC_SOFTMAX_CE);
-      const int blocks = (int)ceil_div(bs, 8);
-      softmax_ce_kernel<<<blocks, 256, 0, c->stream>>>(c->d_probs, bs, c->C, c->ldw[c->L + 1], labels, nullptr,
-                                                       c->d_dz[c->L], nullptr, nullptr, c->d_stats);
-      PB_CUDA(cudaGetLastError());
-    }
+    PB_TRY(zero_grads(c));
+    // probs are not written during training; dZ goes to its own buffer
+    PB_TRY(softmax_ce(c, bs, labels, false, true, false, true, true, advance));
     PB_TRY(backward(c, x, bs));
-  } else {
+  } else {   // empty shard on this rank: contribute zero gradients, still advance the cursor
+    PB_TRY(zero_grads(c));
     LaunchScope ls(c, KC_MISC);
-    PB_CUDA(cudaMemsetAsync(c->d_grads, 0, sizeof(float) * c->P, c->stream));
+    StepBookkeeping bk{c->d_norm2, (int)c->tensors.size(), c->d_cursor, advance};
+    step_bookkeeping_kernel<<<1, 256, 0, c->stream>>>(bk);
+    PB_CUDA(cudaGetLastError());
   }
   if (update) {
     PB_TRY(allreduce_grads(c));
@@ -301,13 +311,6 @@ int gather_batch(pycnn_b200_ctx* c, const int64_t* d_idx, const int64_t* cursor,
   const int64_t total = (int64_t)bs * (c->Dp >> 2);
   gather_rows_kernel<<<grid_for(total, 256, c->num_sms), 256, 0, c->stream>>>(c->d_feat, c->d_labels, d_idx, cursor, extra, bs,
                                                                               c->Dp, c->d_x, c->d_blabels);
-  PB_CUDA(cudaGetLastError());
-  return 0;
-}
-
-int advance_cursor(pycnn_b200_ctx* c, int64_t advance) {
-  LaunchScope ls(c, KC_MISC);
-  advance_cursor_kernel<<<1, 1, 0, c->stream>>>(c->d_cursor, advance);
   PB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -356,8 +359,7 @@ enum GraphKind { GK_STEP_ROWS = 1, GK_STEP_IMAGES = 2 };
 int graphed_step_rows(pycnn_b200_ctx* c, int bs, int64_t lo, int64_t advance) {
   return run_graphed(c, std::make_tuple((int)GK_STEP_ROWS, (int64_t)bs, lo, advance, 0), [&]() -> int {
     PB_TRY(gather_batch(c, c->d_idx, c->d_cursor, lo, bs));
-    PB_TRY(step_on_batch(c, c->d_x, c->d_blabels, bs, true));
-    PB_TRY(advance_cursor(c, advance));
+    PB_TRY(step_on_batch(c, c->d_x, c->d_blabels, bs, true, advance));
     return 0;
   });
 }
@@ -931,7 +933,6 @@ int pycnn_b200_train_step_images(pycnn_b200_ctx* c, const uint8_t* images, const
   PB_TRY(run_graphed(c, std::make_tuple((int)GK_STEP_IMAGES, (int64_t)n, (int64_t)S, (int64_t)0, 0), [&]() -> int {
     PB_TRY(extract_device(c, c->d_images, n, S, c->d_x, c->Dp));
     PB_TRY(step_on_batch(c, c->d_x, c->d_blabels, n, true));
-    PB_TRY(advance_cursor(c, 0));
     return 0;
   }));
   if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += 1;
@@ -959,7 +960,6 @@ int pycnn_b200_apply_update(pycnn_b200_ctx* c) {
   CTX_GUARD(c);
   PB_CHECK(c->d_params, "set_network must be called first");
   PB_TRY(apply_update(c));
-  PB_TRY(advance_cursor(c, 0));
   if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += 1;
   return 0;
 }
@@ -1040,12 +1040,7 @@ int pycnn_b200_evaluate_rows(pycnn_b200_ctx* c, int64_t row0, int64_t n, int bat
   for (int64_t s = 0; s < n; s += batch_size) {   // pycnn/pycnn.py:888-898
     const int bs = (int)std::min<int64_t>(batch_size, n - s);
     PB_TRY(forward_logits(c, c->d_feat + (row0 + s) * c->Dp, bs));
-    {
-      LaunchScope ls(c, KC_SOFTMAX_CE);
-      softmax_ce_kernel<<<(unsigned)ceil_div(bs, 8), 256, 0, c->stream>>>(c->d_probs, bs, c->C, c->ldw[c->L + 1], c->d_labels + row0 + s,
-                                                                          nullptr, nullptr, c->d_pred, nullptr, c->d_stats);
-      PB_CUDA(cudaGetLastError());
-    }
+    PB_TRY(softmax_ce(c, bs, c->d_labels + row0 + s, false, false, true, true));
     if (predicted) {
       PB_CUDA(cudaMemcpyAsync(predicted + s, c->d_pred, sizeof(int32_t) * bs, cudaMemcpyDeviceToHost, c->stream));
       PB_CUDA(cudaStreamSynchronize(c->stream));
@@ -1072,12 +1067,7 @@ int pycnn_b200_evaluate_images(pycnn_b200_ctx* c, const uint8_t* images, const i
     PB_CUDA(cudaMemcpyAsync(c->d_img_labels, labels + s, sizeof(int32_t) * bs, cudaMemcpyHostToDevice, c->stream));
     PB_TRY(extract_device(c, c->d_images, bs, S, c->d_x, c->Dp));
     PB_TRY(forward_logits(c, c->d_x, bs));
-    {
-      LaunchScope ls(c, KC_SOFTMAX_CE);
-      softmax_ce_kernel<<<(unsigned)ceil_div(bs, 8), 256, 0, c->stream>>>(c->d_probs, bs, c->C, c->ldw[c->L + 1], c->d_img_labels,
-                                                                          nullptr, nullptr, c->d_pred, nullptr, c->d_stats);
-      PB_CUDA(cudaGetLastError());
-    }
+    PB_TRY(softmax_ce(c, bs, c->d_img_labels, false, false, true, true));
     if (predicted) PB_CUDA(cudaMemcpyAsync(predicted + s, c->d_pred, sizeof(int32_t) * bs, cudaMemcpyDeviceToHost, c->stream));
     PB_CUDA(cudaStreamSynchronize(c->stream));  // staging buffers are reused by the next chunk
   }
@@ -1094,12 +1084,8 @@ int pycnn_b200_backward_last(pycnn_b200_ctx* c, const int32_t* labels, int bs) {
   // forward to regenerate logits from the activations' inputs (cheap at the sizes this compat path sees)
   PB_TRY(forward_logits(c, c->d_x, bs));
   PB_TRY(zero_stats(c));
-  {
-    LaunchScope ls(c, KC_SOFTMAX_CE);
-    softmax_ce_kernel<<<(unsigned)ceil_div(bs, 8), 256, 0, c->stream>>>(c->d_probs, bs, c->C, c->ldw[c->L + 1], c->d_blabels, nullptr,
-                                                                        c->d_dz[c->L], nullptr, nullptr, c->d_stats);
-    PB_CUDA(cudaGetLastError());
-  }
+  PB_TRY(zero_grads(c));
+  PB_TRY(softmax_ce(c, bs, c->d_blabels, false, true, false, true, true, 0));
   PB_TRY(backward(c, c->d_x, bs));
   PB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

@@ -68,14 +68,36 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
 // stats[0] += sum of row losses (double); stats[1] += #correct (as a double, exact below 2^53).
 // Any of probs/dz/pred/conf may be null.  labels may be null (inference: no loss/dz).
 // ---------------------------------------------------------------------------------------------
+struct StepBookkeeping {   // per-step housekeeping folded into the softmax kernel (block 0) to save graph nodes
+  double* norm2;           // per-tensor squared-norm accumulators to zero for this step's grad_sqnorm_kernel
+  int n_norm;
+  int64_t* cursor;         // cursor[0] += advance (next batch of the permutation); cursor[1] += 1 (step count t)
+  int64_t advance;
+};
+
+__global__ void step_bookkeeping_kernel(StepBookkeeping bk) {   // ranks whose shard of a batch is empty
+  if (bk.norm2 && (int)threadIdx.x < bk.n_norm) bk.norm2[threadIdx.x] = 0.0;
+  if (bk.cursor && threadIdx.x == 0) { bk.cursor[0] += bk.advance; bk.cursor[1] += 1; }
+}
+
 __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict__ logits, int bs, int C,
                                                          int64_t ld, const int32_t* __restrict__ labels,
                                                          float* __restrict__ probs, float* __restrict__ dz,
                                                          int32_t* __restrict__ pred, float* __restrict__ conf,
-                                                         double* __restrict__ stats) {
+                                                         double* __restrict__ stats, float* __restrict__ db,
+                                                         StepBookkeeping bk) {
+  extern __shared__ float s_db[];   // [C] when db != nullptr: block-level bias-gradient partial sums
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (blockIdx.x == 0) {
+    if (bk.norm2 && threadIdx.x < bk.n_norm) bk.norm2[threadIdx.x] = 0.0;
+    if (bk.cursor && threadIdx.x == 0) { bk.cursor[0] += bk.advance; bk.cursor[1] += 1; }
+  }
+  if (db) {
+    for (int j = threadIdx.x; j < C; j += blockDim.x) s_db[j] = 0.f;
+    __syncthreads();
+  }
   double my_loss = 0.0;
   unsigned long long my_correct = 0ull;
   if (row < bs) {
@@ -102,7 +124,9 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
       float p = 0.f;
       if (j < C) p = expf(z[j] - mx) * inv;
       if (probs) probs[(int64_t)row * ld + j] = p;
-      if (dz) dz[(int64_t)row * ld + j] = (j < C) ? (p - (j == y ? 1.0f : 0.0f)) : 0.0f;
+      const float d = (j < C) ? (p - (j == y ? 1.0f : 0.0f)) : 0.0f;
+      if (dz) dz[(int64_t)row * ld + j] = d;
+      if (db && j < C) atomicAdd(&s_db[j], d);           // db_o = sum_rows dZ (backward_pass.pyx:72)
       if (j == y) my_loss = -log((double)p + 1e-9);
     }
     if (lane == 0) {
@@ -110,6 +134,10 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
       if (conf) conf[row] = inv;  // p[argmax] = exp(0)/s
       if (y >= 0 && arg == y) my_correct = 1ull;
     }
+  }
+  if (db) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < C; j += blockDim.x) atomicAdd(&db[j], s_db[j]);
   }
   if (stats && labels) {
     // block-level reduction -> one atomic pair per block
@@ -136,7 +164,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
 // when R > 1).  Coalesced 128-byte row segments; R is chosen so the grid fills the SMs.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dz, int bs, int N, int64_t ld,
-                                                     float* __restrict__ db, int rows_per_block) {
+                                                     float* __restrict__ db, int rows_per_block, int accumulate) {
   __shared__ double red[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_block;
@@ -150,7 +178,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-    if (gridDim.y == 1) db[n] = (float)s;
+    if (gridDim.y == 1 && !accumulate) db[n] = (float)s;
     else atomicAdd(&db[n], (float)s);
   }
 }
@@ -189,13 +217,10 @@ struct UpdateParams {
   int rule;      // 0 cpu (clip + skip), 1 cupy
   float lr, beta1, beta2, eps, inv_bc1, inv_bc2, eps2, max_norm;
   double beta1_d, beta2_d;
-  const int64_t* steps_done;  // device-side count of completed updates (CuPy rule: t = steps_done + 1)
+  const int64_t* steps_done;  // device cursor; [1] = Adam step count t of the current step (CuPy rule)
 };
 
-__global__ void advance_cursor_kernel(int64_t* cursor, int64_t advance) {
-  cursor[0] += advance;
-  cursor[1] += 1;
-}
+
 
 // clipped SGD / Adam over the flat buffers; each block handles one chunk and reads its tensor's norm.
 // CPU rule (gradient_decent.pyx): g *= 5/||g|| when ||g|| > 5 (:33-35); non-finite -> skip tensor
@@ -208,7 +233,7 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ pa
   const Chunk ch = chunks[blockIdx.x];
   float scale = 1.0f;
   if (u.rule == 1 && u.opt == 1) {   // pycnn/pycnn.py:534,544-545: t advances, 1 - beta^t
-    const double t = (double)(u.steps_done[1] + 1);
+    const double t = (double)max((long long)u.steps_done[1], 1ll);   // incremented by this step's softmax kernel
     u.inv_bc1 = (float)(1.0 / (1.0 - pow(u.beta1_d, t)));
     u.inv_bc2 = (float)(1.0 / (1.0 - pow(u.beta2_d, t)));
   }

@@ -50,7 +50,7 @@ struct TcGemmArgs {
   const float* bias;
   const float* mask;
   int64_t ldmask;
-  int mn_variant;    // debug: 1 swaps LBO/SBO of the MN-major descriptors (PYCNN_B200_MN_VARIANT)
+  float* colsum;     // optional: colsum[n] += sum_m C[m,n] of the epilogue output (bias gradient), !atomic only
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -133,8 +133,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           // K-major: advance 8 floats (32 B) inside the 128-B swizzle row; MN-major: next 8 k-rows (1024 B)
           // MN-major TF32 operands only exist in the SWIZZLE_128B_BASE32B form (32-byte swizzle granules,
           // 4 k-rows per 512-B atom): LBO = stride between 32-float MN atoms, SBO = stride between 4-row groups
-          const uint32_t mn_lbo = g.mn_variant ? 512u : (uint32_t)(G_BK * 128);
-          const uint32_t mn_sbo = g.mn_variant ? (uint32_t)(G_BK * 128) : 512u;
+          constexpr uint32_t mn_lbo = G_BK * 128, mn_sbo = 512u;
           const uint64_t da = A_MN ? make_smem_desc(sa + k * 1024, mn_lbo, mn_sbo, UMMA_SWIZZLE_128B_BASE32B)
                                    : make_smem_desc(sa + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
           const uint64_t db = B_MN ? make_smem_desc(sb + k * 1024, mn_lbo, mn_sbo, UMMA_SWIZZLE_128B_BASE32B)
@@ -147,49 +146,84 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else {
     // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+    // 1. tcgen05.ld gives thread i the 32-column chunks of accumulator row i; they are parked in this warp's
+    //    staging tile in the (now idle) operand smem with a pitch of BN+4 floats (conflict-free 128-bit stores);
+    // 2. the warp then walks its 32 rows with lanes along the columns, so bias / mask loads, stores and split-K
+    //    reductions are all coalesced 128-bit accesses; column sums for the bias gradient are taken on the way.
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
+    constexpr int PITCH = BN + 4;
+    float* stage = reinterpret_cast<float*>(smem) + q * 32 * PITCH;
     mbar_wait(tmem_full_bar, 0);
     fence_after_thread_sync();
-    const bool row_ok = row < g.M;
-    float* crow = g.C + (int64_t)row * g.ldc;
-    const float* mrow = (g.epi == 3) ? g.mask + (int64_t)row * g.ldmask : nullptr;
-    const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+    const int ncols = min(BN, g.N - n0);             // valid columns of this tile (warp-uniform)
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
-      if (n0 + c >= g.N) break;  // warp-uniform
+      if (c >= ncols) break;
       float v[32];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
       tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
-      if (row_ok) {
+      float4* dst = reinterpret_cast<float4*>(stage + lane * PITCH + c);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c + j;
-          if (n < g.N) {
-            float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
-            if (!g.atomic) {
+      for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    __syncwarp();
+    const int row0 = m0 + q * 32;
+    const int nrows = min(32, g.M - row0);            // warp-uniform, may be <= 0
+    const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+                        (g.epi != 3 || (((g.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0)));
+#pragma unroll 1
+    for (int cc = lane * 4; cc < ncols; cc += 128) {
+      const int n = n0 + cc;
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!g.atomic && (g.epi == 1 || g.epi == 2)) {
+        bias4.x = __ldg(g.bias + n);
+        bias4.y = (n + 1 < g.N) ? __ldg(g.bias + n + 1) : 0.f;
+        bias4.z = (n + 2 < g.N) ? __ldg(g.bias + n + 2) : 0.f;
+        bias4.w = (n + 3 < g.N) ? __ldg(g.bias + n + 3) : 0.f;
+      }
+      float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int r = 0; r < nrows; ++r) {
+        const float4 acc = *reinterpret_cast<const float4*>(stage + r * PITCH + cc);
+        float o[4] = {acc.x, acc.y, acc.z, acc.w};
+        float* crow = g.C + (int64_t)(row0 + r) * g.ldc + n;
+        if (!g.atomic) {
+          if (g.epi == 1 || g.epi == 2) { o[0] += bias4.x; o[1] += bias4.y; o[2] += bias4.z; o[3] += bias4.w; }
+          if (g.epi == 2) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (n + e < g.N) {
-                  if (g.epi == 1 || g.epi == 2) o[e] += __ldg(g.bias + n + e);
-                  if (g.epi == 2) o[e] = (o[e] < 0.f) ? 0.f : o[e];
-                  if (g.epi == 3) o[e] = (__ldg(mrow + n + e) <= 0.f) ? 0.f : o[e];
-                }
-              }
-            }
-            if (n + 3 < g.N && vec_ok) {
-              if (g.atomic) red_add_v4(crow + n, o[0], o[1], o[2], o[3]);
-              else *reinterpret_cast<float4*>(crow + n) = make_float4(o[0], o[1], o[2], o[3]);
+            for (int e = 0; e < 4; ++e) o[e] = (o[e] < 0.f) ? 0.f : o[e];
+          }
+          if (g.epi == 3) {
+            const float* mrow = g.mask + (int64_t)(row0 + r) * g.ldmask + n;
+            float mk[4];
+            if (vec_ok) {
+              const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow));
+              mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w;
             } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (n + e < g.N) {
-                  if (g.atomic) atomicAdd(crow + n + e, o[e]);
-                  else crow[n + e] = o[e];
-                }
+              for (int e = 0; e < 4; ++e) mk[e] = (n + e < g.N) ? __ldg(mrow + e) : 0.f;
             }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = (mk[e] <= 0.f) ? 0.f : o[e];
           }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) cs[e] += o[e];
         }
+        if (vec_ok) {   // columns in [N, round_up(N,4)) are padding of the row and receive exact zeros
+          if (g.atomic) red_add_v4(crow, o[0], o[1], o[2], o[3]);
+          else *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (n + e < g.N) {
+              if (g.atomic) atomicAdd(crow + e, o[e]);
+              else crow[e] = o[e];
+            }
+        }
+      }
+      if (g.colsum && !g.atomic && nrows > 0) {   // db[n] += sum over this warp's rows (backward_pass.pyx:93)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < g.N) atomicAdd(g.colsum + n + e, cs[e]);
       }
     }
   }
@@ -264,6 +298,8 @@ struct GemmCall {
   const float* bias;
   const float* mask; int64_t ldmask;
   int cls;  // KernelClass
+  float* colsum;      // optional fused column sums of the output (must be zeroed by the caller)
+  bool c_is_zero;     // caller guarantees C is already zero (skips the split-K memset)
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -312,13 +348,19 @@ static int dispatch_bn(pycnn_b200_ctx* c, int BN, const GemmCall& g, const CUten
 static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   PB_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "tc_gemm: empty problem");
   PB_CHECK(!( !g.a_kmajor && g.b_kmajor), "tc_gemm: (A MN-major, B K-major) is not instantiated");
-  const int BN = g.N <= 32 ? 32 : g.N <= 64 ? 64 : g.N <= 128 ? 128 : 256;
-  const int tiles_m = (int)ceil_div(g.M, tc::G_BM), tiles_n = (int)ceil_div(g.N, BN);
+  int BN = g.N <= 32 ? 32 : g.N <= 64 ? 64 : g.N <= 128 ? 128 : 256;
+  const int tiles_m = (int)ceil_div(g.M, tc::G_BM);
   const int num_kb = (int)ceil_div(g.K, tc::G_BK);
-  // split-K when the tile grid cannot fill the 148 SMs and K is deep enough to amortise the atomics
+  // shallow-K problems are epilogue/latency bound: prefer narrower tiles so that more SMs share the epilogue
+  // (the A tile is then re-read from L2 once per N tile, which is cheap when K is small)
+  if (num_kb <= 16)
+    while (BN > 32 && tiles_m * (int)ceil_div(g.N, BN) < c->num_sms) BN >>= 1;
+  const int tiles_n = (int)ceil_div(g.N, BN);
+  // deep-K problems whose tile grid cannot fill the 148 SMs: split K across gridDim.z, partial sums meet in
+  // red.global.add.v4.f32 (the epilogue is then applied by gemm_fixup_kernel)
   int split = 1;
   const int tiles = tiles_m * tiles_n;
-  if (tiles * 2 <= c->num_sms && num_kb >= 16) {
+  if (tiles * 2 <= c->num_sms && num_kb >= 16 && !g.colsum) {
     split = (int)std::min<int64_t>(c->num_sms / tiles, num_kb / 8);
     if (split < 1) split = 1;
   }
@@ -334,9 +376,9 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   a.epi = g.epi; a.atomic = split > 1 ? 1 : 0;
   a.num_kb = num_kb; a.kb_per_split = kb_per_split;
   a.bias = g.bias; a.mask = g.mask; a.ldmask = g.ldmask;
-  { const char* v = getenv("PYCNN_B200_MN_VARIANT"); a.mn_variant = (v && v[0] == '1') ? 1 : 0; }
+  a.colsum = g.colsum;
   dim3 grid(tiles_n, tiles_m, split);
-  if (split > 1) {
+  if (split > 1 && !g.c_is_zero) {
     LaunchScope ls(c, KC_MISC);
     PB_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * ((size_t)(g.M - 1) * g.ldc + g.N), c->stream));
   }
