@@ -708,7 +708,7 @@ int pycnn_b200_set_network(pycnn_b200_ctx* c, int64_t D, const int* layers, int 
   PB_TRY(alloc_f32(&c->d_m, c->P));
   PB_TRY(alloc_f32(&c->d_v, c->P));
   std::vector<Chunk> chunks;
-  const int64_t kChunk = 8192;
+  const int64_t kChunk = 2048;   // one 256-thread block per chunk: >= 4 waves of blocks at 1.1 M parameters
   for (size_t t = 0; t < c->tensors.size(); ++t) {
     const int64_t len = c->tensors[t].rows * c->tensors[t].ld;
     for (int64_t o = 0; o < len; o += kChunk) chunks.push_back({(int)t, 0, c->tensors[t].off + o, std::min(kChunk, len - o)});

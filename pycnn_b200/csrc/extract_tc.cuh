@@ -40,6 +40,22 @@ constexpr int MAX_F = 64;          // 4*F <= 256 accumulator columns per stage
 constexpr int THREADS = 320;
 constexpr int B_BYTES_MAX = 256 * 32;
 
+struct FastDiv {   // n / d for n < 2^31 by multiply-high: q = umulhi(n, mul) >> shift   (d == 1: mul == 0)
+  uint32_t mul, shift, d;
+};
+__host__ inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{0u, 0u, d};
+  if (d <= 1) return f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;                                  // l = ceil(log2 d) >= 1
+  f.mul = (uint32_t)((((unsigned long long)1 << (31 + l)) + d - 1) / d);   // ceil(2^(31+l) / d) < 2^32
+  f.shift = l - 1;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  return f.mul ? (__umulhi(n, f.mul) >> f.shift) : n;
+}
+
 struct ExArgs {
   const uint8_t* images;
   float* out;
@@ -47,6 +63,7 @@ struct ExArgs {
   int R;          // total pooled positions (rows) = n * PP
   int num_tiles;  // ceil(R / 128)
   int S, PW, PP;
+  FastDiv div_pp, div_pw;
   int F, N;       // N = 4 * round_up(F, 4) accumulator columns
   int has_lo;
   int stage_cols; // TMEM columns per accumulator stage (tmem_cols / 2)
@@ -65,8 +82,8 @@ struct Span {
 __device__ __forceinline__ Span tile_span(const ExArgs& a, int t) {
   const uint32_t r0 = (uint32_t)t * 128u;
   const uint32_t r1 = min((uint32_t)a.R, r0 + 128u) - 1u;
-  const uint32_t img0 = r0 / a.PP, py0 = (r0 - img0 * a.PP) / a.PW;
-  const uint32_t img1 = r1 / a.PP, py1 = (r1 - img1 * a.PP) / a.PW;
+  const uint32_t img0 = fdiv(r0, a.div_pp), py0 = fdiv(r0 - img0 * a.PP, a.div_pw);
+  const uint32_t img1 = fdiv(r1, a.div_pp), py1 = fdiv(r1 - img1 * a.PP, a.div_pw);
   const uint32_t SS = (uint32_t)a.S * a.S;
   Span s;
   s.g0 = img0 * SS + 2u * py0 * a.S;
@@ -85,7 +102,7 @@ __device__ __forceinline__ uint32_t pack_sums_to_half2(uint32_t s_lo, uint32_t s
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(THREADS, 2) extract_tc_kernel(const ExArgs a) {
+__global__ void __launch_bounds__(THREADS, 2) extract_tc_kernel(const __grid_constant__ ExArgs a) {
   extern __shared__ uint8_t smem_raw_[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_) + 127) & ~uintptr_t(127));
   uint8_t* raw = smem;                                      // RAW_STAGES x RAW_BYTES
@@ -101,6 +118,7 @@ __global__ void __launch_bounds__(THREADS, 2) extract_tc_kernel(const ExArgs a) 
   uint64_t* tmem_full = a_empty + A_STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint2* span_info = reinterpret_cast<uint2*>(tmem_slot + 2);     // [RAW_STAGES] {g0, shift} of the staged span
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -125,36 +143,45 @@ __global__ void __launch_bounds__(THREADS, 2) extract_tc_kernel(const ExArgs a) 
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot;
+  const int tile_step = gridDim.x;
 
   if (warp == 0) {
-    // ===== producer: one bulk copy per tile =====
+    // ===== producer: one bulk copy per tile; publishes {g0, shift} of the span next to the data =====
     if (lane == 0) {
-      int i = 0;
-      for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++i) {
-        const int s = i % RAW_STAGES;
-        tc::mbar_wait(&raw_empty[s], ((i / RAW_STAGES) & 1) ^ 1);
+      int s = 0;
+      uint32_t ph = 1;   // parity to wait for on raw_empty: first pass falls through
+      for (int t = blockIdx.x; t < a.num_tiles; t += tile_step) {
+        tc::mbar_wait(&raw_empty[s], ph);
         const Span sp = tile_span(a, t);
-        tc::mbar_arrive_expect_tx(&raw_full[s], sp.bytes);
+        span_info[s] = make_uint2(sp.g0, sp.shift);
+        tc::mbar_arrive_expect_tx(&raw_full[s], sp.bytes);     // release: span_info is visible to waiters
         tc::bulk_load(raw + s * RAW_BYTES, a.images + sp.b0, sp.bytes, &raw_full[s]);
+        if (++s == RAW_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp <= 4) {
     // ===== builders: thread m builds row m of the A tile =====
     const int m = threadIdx.x - 32;
-    int i = 0;
-    for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++i) {
-      const int sr = i % RAW_STAGES, sa = i % A_STAGES;
-      const Span sp = tile_span(a, t);
+    int sr = 0, sa = 0;
+    uint32_t ph_r = 0, ph_a = 1;
+    const uint32_t SS = (uint32_t)a.S * a.S, S3 = 3u * a.S;
+    uint8_t* const arow0 = a_ring + (m >> 3) * 256 + (m & 7) * 16;
+    for (int t = blockIdx.x; t < a.num_tiles; t += tile_step) {
       const uint32_t r = (uint32_t)t * 128u + m;
       uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      tc::mbar_wait(&raw_full[sr], (i / RAW_STAGES) & 1);
-      if (r < (uint32_t)a.R) {
-        const uint32_t img = r / a.PP, p = r - img * a.PP, py = p / a.PW, px = p - py * a.PW;
-        const uint32_t pix = img * (uint32_t)a.S * a.S + 2u * py * a.S + 2u * px - sp.g0;
+      uint32_t pix = 0;
+      const bool valid = r < (uint32_t)a.R;
+      if (valid) {   // position decode overlaps the wait for the raw bytes
+        const uint32_t img = fdiv(r, a.div_pp), p = r - img * a.PP, py = fdiv(p, a.div_pw), px = p - py * a.PW;
+        pix = img * SS + 2u * py * a.S + 2u * px;
+      }
+      tc::mbar_wait(&raw_full[sr], ph_r);
+      if (valid) {
+        const uint2 info = span_info[sr];
         const uint32_t* words = reinterpret_cast<const uint32_t*>(raw + sr * RAW_BYTES);
-        uint32_t off = sp.shift + 3u * pix;
+        uint32_t off = info.y + 3u * (pix - info.x);
 #pragma unroll
-        for (int u = 0; u < 4; ++u, off += 3u * a.S) {
+        for (int u = 0; u < 4; ++u, off += S3) {
           const uint32_t w = off >> 2, sh = (off & 3u) * 8u;
           const uint32_t x0 = words[w], x1 = words[w + 1], x2 = words[w + 2], x3 = words[w + 3];
           const uint32_t W0 = __funnelshift_r(x0, x1, sh), W1 = __funnelshift_r(x1, x2, sh),
@@ -168,13 +195,15 @@ __global__ void __launch_bounds__(THREADS, 2) extract_tc_kernel(const ExArgs a) 
           h[2 * u + 1] = pack_sums_to_half2(s2, s3);
         }
       }
-      tc::mbar_wait(&a_empty[sa], ((i / A_STAGES) & 1) ^ 1);
-      uint8_t* arow = a_ring + sa * A_BYTES + (m >> 3) * 256 + (m & 7) * 16;
+      tc::mbar_wait(&a_empty[sa], ph_a);
+      uint8_t* arow = arow0 + sa * A_BYTES;
       *reinterpret_cast<uint4*>(arow) = make_uint4(h[0], h[1], h[2], h[3]);        // k = 0..7  (u = 0,1)
       *reinterpret_cast<uint4*>(arow + 128) = make_uint4(h[4], h[5], h[6], h[7]);  // k = 8..15 (u = 2,3)
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&a_full[sa]);
       tc::mbar_arrive(&raw_empty[sr]);
+      if (++sr == RAW_STAGES) { sr = 0; ph_r ^= 1; }
+      if (++sa == A_STAGES) { sa = 0; ph_a ^= 1; }
     }
   } else if (warp == 5) {
     // ===== MMA issuer =====
@@ -182,54 +211,56 @@ __global__ void __launch_bounds__(THREADS, 2) extract_tc_kernel(const ExArgs a) 
       const uint32_t idesc = tc::make_idesc(tc::FMT_F16, 128, a.N, false, false);
       const uint64_t dbh = tc::make_smem_desc(tc::smem_u32(b_hi), 128, 256, tc::UMMA_SWIZZLE_NONE);
       const uint64_t dbl = tc::make_smem_desc(tc::smem_u32(b_lo), 128, 256, tc::UMMA_SWIZZLE_NONE);
-      int i = 0;
-      for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++i) {
-        const int sa = i % A_STAGES, acc = i & 1;
-        tc::mbar_wait(&tmem_empty[acc], ((i >> 1) & 1) ^ 1);
-        tc::mbar_wait(&a_full[sa], (i / A_STAGES) & 1);
+      const uint64_t da0 = tc::make_smem_desc(tc::smem_u32(a_ring), 128, 256, tc::UMMA_SWIZZLE_NONE);
+      int sa = 0, acc = 0;
+      uint32_t ph_a = 0, ph_t = 1;
+      for (int t = blockIdx.x; t < a.num_tiles; t += tile_step) {
+        tc::mbar_wait(&tmem_empty[acc], ph_t);
+        tc::mbar_wait(&a_full[sa], ph_a);
         tc::fence_after_thread_sync();
-        const uint64_t da = tc::make_smem_desc(tc::smem_u32(a_ring + sa * A_BYTES), 128, 256, tc::UMMA_SWIZZLE_NONE);
+        const uint64_t da = da0 + (uint64_t)((sa * A_BYTES) >> 4);   // start-address field is in 16-byte units
         const uint32_t d = tmem_base + (uint32_t)(acc * a.stage_cols);
         tc::mma_f16(d, da, dbh, idesc, 0u);
         if (a.has_lo) tc::mma_f16(d, da, dbl, idesc, 1u);
         tc::mma_commit(&a_empty[sa]);
         tc::mma_commit(&tmem_full[acc]);
+        if (++sa == A_STAGES) { sa = 0; ph_a ^= 1; }
+        if (++acc == 2) { acc = 0; ph_t ^= 1; }
       }
     }
   } else {
     // ===== epilogue (warps 6..9): TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    int i = 0;
-    for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++i) {
-      const int acc = i & 1;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    int acc = 0;
+    uint32_t ph_t = 0;
+    const int nchunks = a.N >> 4;
+    for (int t = blockIdx.x; t < a.num_tiles; t += tile_step) {
       const uint32_t r = (uint32_t)t * 128u + m;
       const bool valid = r < (uint32_t)a.R;
-      const uint32_t img = valid ? r / a.PP : 0u, p = valid ? r - img * a.PP : 0u;
+      const uint32_t img = valid ? fdiv(r, a.div_pp) : 0u, p = valid ? r - img * a.PP : 0u;
       float* o = a.out + (int64_t)img * a.ld + p;
-      tc::mbar_wait(&tmem_full[acc], (i >> 1) & 1);
+      tc::mbar_wait(&tmem_full[acc], ph_t);
       tc::fence_after_thread_sync();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)(acc * a.stage_cols);
+      const uint32_t taddr = lane_base + (uint32_t)(acc * a.stage_cols);
+      int f = 0;
 #pragma unroll 1
-      for (int c = 0; c < a.N; c += 16) {
+      for (int c = 0; c < nchunks; ++c) {
         float v[16];
         __syncwarp();
-        tc::tmem_ld16(taddr + c, v);
-        if (valid) {
+        tc::tmem_ld16(taddr + c * 16, v);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int f = (c >> 2) + j;
-            if (f < a.F) {
-              float mx = fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3]));
-              mx = fmaxf(mx, 0.f);
-              o[(int64_t)f * a.PP] = mx * s_scale[f];
-            }
-          }
+        for (int j = 0; j < 4; ++j, ++f, o += a.PP) {
+          float mx = fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3]));
+          mx = fmaxf(mx, 0.f) * s_scale[f];      // s_scale is padded to MAX_F: no bound check on the load
+          if (valid && f < a.F) *o = mx;
         }
       }
       __syncwarp();
       tc::fence_before_thread_sync();
       tc::mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; ph_t ^= 1; }
     }
   }
   tc::fence_before_thread_sync();
@@ -240,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 2) extract_tc_kernel(const ExArgs a) 
   }
 }
 
-constexpr int SMEM_BYTES = RAW_STAGES * RAW_BYTES + A_STAGES * A_BYTES + 2 * B_BYTES_MAX + MAX_F * 4 + 256 + 128;
+constexpr int SMEM_BYTES = RAW_STAGES * RAW_BYTES + A_STAGES * A_BYTES + 2 * B_BYTES_MAX + MAX_F * 4 + 320 + 128;
 
 }  // namespace tcx
 
@@ -337,6 +368,7 @@ static inline int tc_extract(pycnn_b200_ctx* c, const uint8_t* d_images, int64_t
     a.R = (int)(nb * PP);
     a.num_tiles = (int)ceil_div(a.R, 128);
     a.S = S; a.PW = PW; a.PP = PP;
+    a.div_pp = tcx::make_fastdiv((uint32_t)PP); a.div_pw = tcx::make_fastdiv((uint32_t)PW);
     a.F = c->F; a.N = N; a.has_lo = c->tc_ncols > 0 ? 1 : 0;
     a.tmem_cols = tmem_cols; a.stage_cols = tmem_cols / 2;
     a.bpack = static_cast<const uint8_t*>(c->d_tc_filters);

@@ -170,60 +170,91 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int nrows = min(32, g.M - row0);            // warp-uniform, may be <= 0
     const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
                         (g.epi != 3 || (((g.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0)));
+    // lane -> (row, 4 columns): LPR lanes cover one row segment, RPI rows are handled per iteration and U
+    // iterations are batched so that U independent mask loads are in flight per lane
+    constexpr int LPR = (BN >= 128) ? 32 : BN / 4;
+    constexpr int RPI = 32 / LPR;
+    constexpr int U = (RPI == 1) ? 8 : 4;
+    constexpr int PASSES = (BN + 127) / 128;
+    const int lr = lane / LPR, lc = (lane % LPR) * 4;
 #pragma unroll 1
-    for (int cc = lane * 4; cc < ncols; cc += 128) {
+    for (int pass = 0; pass < PASSES; ++pass) {
+      const int cc = pass * 128 + lc;
+      const bool col_ok = cc < ncols;
       const int n = n0 + cc;
-      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!g.atomic && (g.epi == 1 || g.epi == 2)) {
-        bias4.x = __ldg(g.bias + n);
-        bias4.y = (n + 1 < g.N) ? __ldg(g.bias + n + 1) : 0.f;
-        bias4.z = (n + 2 < g.N) ? __ldg(g.bias + n + 2) : 0.f;
-        bias4.w = (n + 3 < g.N) ? __ldg(g.bias + n + 3) : 0.f;
+      float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (col_ok && !g.atomic && (g.epi == 1 || g.epi == 2)) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) bias4[e] = (n + e < g.N) ? __ldg(g.bias + n + e) : 0.f;
       }
       float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int r = 0; r < nrows; ++r) {
-        const float4 acc = *reinterpret_cast<const float4*>(stage + r * PITCH + cc);
-        float o[4] = {acc.x, acc.y, acc.z, acc.w};
-        float* crow = g.C + (int64_t)(row0 + r) * g.ldc + n;
-        if (!g.atomic) {
-          if (g.epi == 1 || g.epi == 2) { o[0] += bias4.x; o[1] += bias4.y; o[2] += bias4.z; o[3] += bias4.w; }
-          if (g.epi == 2) {
+      for (int rb = 0; rb < 32; rb += U * RPI) {
+        float mk[U][4];
+        if (g.epi == 3 && !g.atomic) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = (o[e] < 0.f) ? 0.f : o[e];
+          for (int u = 0; u < U; ++u) {
+            const int r = rb + u * RPI + lr;
+            if (col_ok && r < nrows) {
+              const float* mrow = g.mask + (int64_t)(row0 + r) * g.ldmask + n;
+              if (vec_ok) {
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow));
+                mk[u][0] = m4.x; mk[u][1] = m4.y; mk[u][2] = m4.z; mk[u][3] = m4.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) mk[u][e] = (n + e < g.N) ? __ldg(mrow + e) : 0.f;
+              }
+            }
           }
-          if (g.epi == 3) {
-            const float* mrow = g.mask + (int64_t)(row0 + r) * g.ldmask + n;
-            float mk[4];
-            if (vec_ok) {
-              const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow));
-              mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = rb + u * RPI + lr;
+          if (col_ok && r < nrows) {
+            const float4 acc = *reinterpret_cast<const float4*>(stage + r * PITCH + cc);
+            float o[4] = {acc.x, acc.y, acc.z, acc.w};
+            float* crow = g.C + (int64_t)(row0 + r) * g.ldc + n;
+            if (!g.atomic) {
+              if (g.epi == 1 || g.epi == 2) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] += bias4[e];
+              }
+              if (g.epi == 2) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = (o[e] < 0.f) ? 0.f : o[e];
+              }
+              if (g.epi == 3) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = (mk[u][e] <= 0.f) ? 0.f : o[e];
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) cs[e] += o[e];
+            }
+            if (vec_ok) {   // columns in [N, round_up(N,4)) are padding of the row and receive exact zeros
+              if (g.atomic) red_add_v4(crow, o[0], o[1], o[2], o[3]);
+              else *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) mk[e] = (n + e < g.N) ? __ldg(mrow + e) : 0.f;
+              for (int e = 0; e < 4; ++e)
+                if (n + e < g.N) {
+                  if (g.atomic) atomicAdd(crow + e, o[e]);
+                  else crow[e] = o[e];
+                }
             }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = (mk[e] <= 0.f) ? 0.f : o[e];
           }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) cs[e] += o[e];
-        }
-        if (vec_ok) {   // columns in [N, round_up(N,4)) are padding of the row and receive exact zeros
-          if (g.atomic) red_add_v4(crow, o[0], o[1], o[2], o[3]);
-          else *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (n + e < g.N) {
-              if (g.atomic) atomicAdd(crow + e, o[e]);
-              else crow[e] = o[e];
-            }
         }
       }
-      if (g.colsum && !g.atomic && nrows > 0) {   // db[n] += sum over this warp's rows (backward_pass.pyx:93)
+      if (g.colsum && !g.atomic) {   // db[n] += sum over this warp's 32 rows (backward_pass.pyx:93)
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (n + e < g.N) atomicAdd(g.colsum + n + e, cs[e]);
+        for (int e = 0; e < 4; ++e) {
+#pragma unroll
+          for (int o = LPR; o < 32; o <<= 1) cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], o);
+        }
+        if (lr == 0 && col_ok && nrows > 0) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (n + e < g.N) atomicAdd(g.colsum + n + e, cs[e]);
+        }
       }
     }
   }
@@ -361,7 +392,7 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   int split = 1;
   const int tiles = tiles_m * tiles_n;
   if (tiles * 2 <= c->num_sms && num_kb >= 16 && !g.colsum) {
-    split = (int)std::min<int64_t>(c->num_sms / tiles, num_kb / 8);
+    split = (int)std::min<int64_t>(c->num_sms / tiles, num_kb / 4);
     if (split < 1) split = 1;
   }
   int kb_per_split = (int)ceil_div(num_kb, split);

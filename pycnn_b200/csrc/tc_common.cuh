@@ -39,13 +39,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped launch (an error code to the host), never as
-// a hung GPU.  ~2^31 cycles (~1 s) is far beyond any legitimate wait in these kernels.
+// Bounded wait: a protocol bug must surface as a trapped launch (an error code to the host), never as a
+// hung GPU.  try_wait suspends the thread in hardware for up to the hinted time, so the poll loop costs few
+// issue slots; the bound is a poll count (~seconds), far beyond any legitimate wait in these kernels.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 31)) __trap();
+  uint32_t polls = 0;
+  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
+    if (++polls > (1u << 22)) __trap();
   }
 }
 
