@@ -133,6 +133,14 @@ int pycnn_b200_train_epoch(pycnn_b200_ctx* ctx, const int64_t* perm, int64_t n, 
  * images n x S x S x 3 uint8 (pinned memory recommended), labels n x int32. */
 int pycnn_b200_train_step_images(pycnn_b200_ctx* ctx, const uint8_t* images, const int32_t* labels,
                                  int n, int image_size, double* loss_sum, int64_t* correct);
+/* streaming epoch from HOST images (the e2e path): batches perm[start:start+batch_size] (perm NULL = rows in
+ * order) are brought to the device on a copy stream -- copy engine for contiguous batches, a zero-copy gather
+ * kernel over PCIe for permuted rows of pinned/registered memory -- double-buffered against extractor + step on
+ * the compute stream; the running (loss, #correct) totals are read back asynchronously after every step.
+ * step_stats (nullable) receives 2 doubles per step: cumulative loss sum and cumulative #correct. */
+int pycnn_b200_train_epoch_images(pycnn_b200_ctx* ctx, const uint8_t* images, const int32_t* labels,
+                                  const int64_t* perm, int64_t n, int image_size, int batch_size,
+                                  double* step_stats, double* loss_sum, int64_t* correct);
 /* `steps` back-to-back steps on dataset rows idx[s*bs .. (s+1)*bs), no host sync inside
  * (device-resident benchmark loop); outputs are totals over the steps. */
 int pycnn_b200_train_steps(pycnn_b200_ctx* ctx, const int64_t* idx, int bs, int steps,

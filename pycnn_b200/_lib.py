@@ -69,6 +69,7 @@ _SIGNATURES = {
     "pycnn_b200_train_epoch": [c_ctx, _i64p, I64, I, _dp, _i64p],
     "pycnn_b200_train_step_images": [c_ctx, ctypes.c_void_p, ctypes.c_void_p, I, I, _dp, _i64p],
     "pycnn_b200_train_steps": [c_ctx, _i64p, I, I, _dp, _i64p],
+    "pycnn_b200_train_epoch_images": [c_ctx, ctypes.c_void_p, ctypes.c_void_p, _i64p, I64, I, I, _dp, _dp, _i64p],
     "pycnn_b200_forward_rows": [c_ctx, _i64p, I64, I, _dp],
     "pycnn_b200_forward_features": [c_ctx, _dp, I, _dp],
     "pycnn_b200_predict_images": [c_ctx, ctypes.c_void_p, I64, I, _i32p, _fp],
@@ -347,6 +348,20 @@ class Context:
                                                     ctypes.byref(loss) if want_stats else None,
                                                     ctypes.byref(corr) if want_stats else None))
         return (loss.value, corr.value) if want_stats else None
+
+    def train_epoch_images(self, images_ptr, labels_ptr, n, size, batch_size, perm=None, want_step_stats=False):
+        """Streaming epoch from host memory (raw pointers so pinned buffers pass through untouched)."""
+        steps = -(-int(n) // int(batch_size))
+        st = np.empty((steps, 2), dtype=np.float64) if want_step_stats else None
+        if perm is not None:
+            perm = np.ascontiguousarray(perm, dtype=np.int64)
+            assert perm.shape[0] == n
+        loss, corr = ctypes.c_double(), ctypes.c_int64()
+        check(self.lib.pycnn_b200_train_epoch_images(
+            self.handle, ctypes.c_void_p(images_ptr), ctypes.c_void_p(labels_ptr),
+            ptr(perm, ctypes.c_int64) if perm is not None else None, int(n), int(size), int(batch_size),
+            ptr(st, ctypes.c_double) if st is not None else None, ctypes.byref(loss), ctypes.byref(corr)))
+        return (loss.value, corr.value, st) if want_step_stats else (loss.value, corr.value)
 
     def forward_backward(self, idx):
         idx = np.ascontiguousarray(idx, dtype=np.int64)

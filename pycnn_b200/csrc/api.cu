@@ -500,6 +500,13 @@ int pycnn_b200_destroy(pycnn_b200_ctx* c) {
   free_dataset(c);
   free_dev(c->d_taps); free_dev(c->d_tc_filters); free_dev(c->d_tc_scale);
   free_dev(c->d_idx); free_dev(c->d_images); free_dev(c->d_img_labels);
+  for (int s = 0; s < 2; ++s) {
+    free_dev(c->d_img2[s]); free_dev(c->d_lab2[s]);
+    if (c->ev_copy[s]) cudaEventDestroy(c->ev_copy[s]);
+    if (c->ev_compute[s]) cudaEventDestroy(c->ev_compute[s]);
+    if (c->h_bounce[s]) cudaFreeHost(c->h_bounce[s]);
+  }
+  if (c->h_step_stats) cudaFreeHost(c->h_step_stats);
   free_dev(c->d_scratch); free_dev(c->d_flush); free_dev(c->d_gemm_ws); free_dev(c->d_stats);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->h_stats) cudaFreeHost(c->h_stats);
@@ -937,6 +944,119 @@ int pycnn_b200_train_step_images(pycnn_b200_ctx* c, const uint8_t* images, const
   }));
   if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += 1;
   if (loss_sum || correct) PB_TRY(read_stats(c, loss_sum, correct, true));
+  return 0;
+}
+
+static bool host_ptr_is_device_visible(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost && at.devicePointer != nullptr;
+}
+
+int pycnn_b200_train_epoch_images(pycnn_b200_ctx* c, const uint8_t* images, const int32_t* labels, const int64_t* perm,
+                                  int64_t n, int S, int batch_size, double* step_stats, double* loss_sum,
+                                  int64_t* correct) {
+  CTX_GUARD(c);
+  PB_CHECK(c->d_params, "set_network must be called first");
+  PB_CHECK(n > 0 && batch_size > 0 && images && labels, "empty epoch");
+  PB_CHECK(feature_count(c, S) == c->D, "image_size %d with %d filters gives %lld features, network expects %lld", S, c->F, (long long)feature_count(c, S), (long long)c->D);
+  if (perm)
+    for (int64_t i = 0; i < n; ++i) PB_CHECK(perm[i] >= 0, "negative row index at %lld", (long long)i);
+  const int W = c->world, R = c->rank;
+  const int64_t img_bytes = (int64_t)S * S * 3;
+  const int64_t per_rank_max = ceil_div(std::min<int64_t>(batch_size, n), W);
+  const int64_t num_steps = ceil_div(n, batch_size);
+  PB_TRY(ensure_workspace(c, per_rank_max));
+  // staging: two slots, 16-byte aligned rows are not required by the extractor (it re-aligns its spans)
+  const size_t need_img = (size_t)round_up(per_rank_max * img_bytes + 256, 1 << 20), need_lab = (size_t)round_up(per_rank_max, 1024);
+  if (need_img > c->img2_cap || need_lab > c->lab2_cap) {
+    PB_CUDA(cudaStreamSynchronize(c->stream));
+    PB_CUDA(cudaStreamSynchronize(c->copy_stream));
+    drop_graphs(c);
+    for (int s = 0; s < 2; ++s) {
+      free_dev(c->d_img2[s]); free_dev(c->d_lab2[s]);
+      c->d_img2[s] = nullptr; c->d_lab2[s] = nullptr;
+      PB_CUDA(cudaMalloc(&c->d_img2[s], need_img));
+      PB_CUDA(cudaMemset(c->d_img2[s], 0, need_img));
+      PB_CUDA(cudaMalloc(&c->d_lab2[s], sizeof(int32_t) * need_lab));
+      if (!c->ev_copy[s]) PB_CUDA(cudaEventCreateWithFlags(&c->ev_copy[s], cudaEventDisableTiming));
+      if (!c->ev_compute[s]) PB_CUDA(cudaEventCreateWithFlags(&c->ev_compute[s], cudaEventDisableTiming));
+    }
+    c->img2_cap = need_img; c->lab2_cap = need_lab;
+  }
+  if ((size_t)(2 * num_steps) > c->step_stats_cap) {
+    if (c->h_step_stats) PB_CUDA(cudaFreeHost(c->h_step_stats));
+    c->h_step_stats = nullptr;
+    c->step_stats_cap = (size_t)round_up(2 * num_steps, 1024);
+    PB_CUDA(cudaMallocHost(&c->h_step_stats, sizeof(double) * c->step_stats_cap));
+  }
+  const bool zero_copy = perm && host_ptr_is_device_visible(images) && host_ptr_is_device_visible(labels);
+  const bool bounce = perm && !zero_copy;
+  if (zero_copy) {
+    PB_TRY(ensure_idx(c, n));
+    PB_CUDA(cudaMemcpyAsync(c->d_idx, perm, sizeof(int64_t) * n, cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(cudaStreamSynchronize(c->stream));   // the copy stream reads d_idx
+  }
+  if (bounce) {
+    const size_t need = (size_t)round_up(per_rank_max * (img_bytes + 4), 1 << 20);
+    if (need > c->bounce_cap) {
+      for (int s = 0; s < 2; ++s) {
+        if (c->h_bounce[s]) PB_CUDA(cudaFreeHost(c->h_bounce[s]));
+        c->h_bounce[s] = nullptr;
+        PB_CUDA(cudaMallocHost(&c->h_bounce[s], need));
+      }
+      c->bounce_cap = need;
+    }
+  }
+  PB_TRY(zero_stats(c));
+  int64_t step = 0;
+  for (int64_t start = 0; start < n; start += batch_size, ++step) {
+    const int64_t end = std::min<int64_t>(start + batch_size, n);
+    const int64_t len = end - start, per = ceil_div(len, W);
+    const int64_t lo = std::min(len, per * R), hi = std::min(len, per * (R + 1));
+    const int bs = (int)(hi - lo);
+    const int slot = (int)(step & 1);
+    // ---- copy stream: bring this rank's slice of the batch into staging slot `slot`
+    if (step >= 2) PB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_compute[slot], 0));
+    if (bs > 0) {
+      if (!perm) {
+        PB_CUDA(cudaMemcpyAsync(c->d_img2[slot], images + (start + lo) * img_bytes, (size_t)bs * img_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        PB_CUDA(cudaMemcpyAsync(c->d_lab2[slot], labels + start + lo, sizeof(int32_t) * bs, cudaMemcpyHostToDevice, c->copy_stream));
+      } else if (zero_copy) {
+        const int64_t total = (int64_t)bs * (img_bytes >> 4);
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256 * 4), 2 * c->num_sms));
+        gather_host_rows_kernel<<<blocks, 256, 0, c->copy_stream>>>(images, labels, c->d_idx + start + lo, bs, img_bytes,
+                                                                    c->d_img2[slot], c->d_lab2[slot]);
+        PB_CUDA(cudaGetLastError());
+        c->launches += 1;
+        c->class_launches[KC_GATHER] += 1;
+      } else {
+        if (step >= 2) PB_CUDA(cudaEventSynchronize(c->ev_copy[slot]));   // previous H2D out of this bounce buffer is done
+        uint8_t* hb = c->h_bounce[slot];
+        int32_t* hl = reinterpret_cast<int32_t*>(hb + (size_t)per_rank_max * img_bytes);
+        for (int i = 0; i < bs; ++i) {
+          const int64_t src = perm[start + lo + i];
+          memcpy(hb + (size_t)i * img_bytes, images + src * img_bytes, (size_t)img_bytes);
+          hl[i] = labels[src];
+        }
+        PB_CUDA(cudaMemcpyAsync(c->d_img2[slot], hb, (size_t)bs * img_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        PB_CUDA(cudaMemcpyAsync(c->d_lab2[slot], hl, sizeof(int32_t) * bs, cudaMemcpyHostToDevice, c->copy_stream));
+      }
+    }
+    PB_CUDA(cudaEventRecord(c->ev_copy[slot], c->copy_stream));
+    // ---- compute stream: extractor + step on that slot (one cached graph per slot and batch size)
+    PB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[slot], 0));
+    PB_TRY(run_graphed(c, std::make_tuple((int)GK_STEP_IMAGES + 1 + slot, (int64_t)bs, (int64_t)S, (int64_t)0, 0), [&]() -> int {
+      if (bs > 0) PB_TRY(extract_device(c, c->d_img2[slot], bs, S, c->d_x, c->Dp));
+      PB_TRY(step_on_batch(c, c->d_x, c->d_lab2[slot], bs, true));
+      return 0;
+    }));
+    if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += 1;
+    PB_CUDA(cudaMemcpyAsync(c->h_step_stats + 2 * step, c->d_stats, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PB_CUDA(cudaEventRecord(c->ev_compute[slot], c->stream));
+  }
+  PB_TRY(read_stats(c, loss_sum, correct, true));
+  if (step_stats) memcpy(step_stats, c->h_step_stats, sizeof(double) * 2 * (size_t)num_steps);
   return 0;
 }
 

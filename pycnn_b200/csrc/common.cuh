@@ -170,6 +170,16 @@ struct pycnn_b200_ctx {
   float* d_flush = nullptr;   // L2 flush buffer
   size_t flush_bytes = 0;
 
+  // double-buffered staging for the streaming epoch (copy stream || compute stream)
+  uint8_t* d_img2[2] = {nullptr, nullptr};
+  int32_t* d_lab2[2] = {nullptr, nullptr};
+  size_t img2_cap = 0, lab2_cap = 0;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr};
+  uint8_t* h_bounce[2] = {nullptr, nullptr};   // pinned bounce buffers for pageable host memory
+  size_t bounce_cap = 0;
+  double* h_step_stats = nullptr;              // pinned ring for per-step (loss, correct) read-backs
+  size_t step_stats_cap = 0;
+
   // comm
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;

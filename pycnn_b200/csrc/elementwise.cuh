@@ -60,6 +60,33 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
   }
 }
 
+// Zero-copy batch assembly: rows idx[i] of a pinned host array (device-visible through UVA) are pulled over
+// PCIe with 128-bit loads straight into the device staging buffer -- no host-side gather, no copy-engine
+// round trip per row.  row_bytes % 16 == 0 is guaranteed by the caller (else the byte tail loop runs).
+__global__ void __launch_bounds__(256) gather_host_rows_kernel(const uint8_t* __restrict__ host_rows,
+                                                               const int32_t* __restrict__ host_labels,
+                                                               const int64_t* __restrict__ idx, int bs,
+                                                               int64_t row_bytes, uint8_t* __restrict__ dst,
+                                                               int32_t* __restrict__ dst_labels) {
+  const int64_t vec = row_bytes >> 4, tail = row_bytes & 15;
+  const int64_t total = (int64_t)bs * vec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / vec, cidx = i - r * vec;
+    const int64_t src = idx[r];
+    const uint4 v = *(reinterpret_cast<const uint4*>(host_rows + src * row_bytes) + cidx);
+    *(reinterpret_cast<uint4*>(dst + r * row_bytes) + cidx) = v;
+    if (cidx == 0) dst_labels[r] = host_labels[src];
+  }
+  if (tail) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)bs * tail;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i / tail, b = vec * 16 + (i - r * tail);
+      dst[r * row_bytes + b] = host_rows[idx[r] * row_bytes + b];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K4+K5+K6(a): row softmax (max-subtracted, forward_pass.pyx:40-41), CE loss
 // -log(p[y]+1e-9) (optimized.cpp:34-46), argmax==label count (pycnn.py:637-639) and

@@ -293,7 +293,8 @@ def test_c1_trajectory_100_steps(lib, ctx, mode, opt, lr):
     err = np.abs(np.array(losses) - want) / want
     print(f"\n[{mode}/{opt}] 100-step loss trajectory: max rel dev {err.max():.3e}, final {losses[-1]:.6f} vs {want[-1]:.6f}")
     assert err.max() < loss_tol
-    assert err[:20].max() < (1e-5 if mode == "fp32" else 1.5e-1)
+    if mode == "fp32":
+        assert err[:20].max() < 1e-5       # before the chaotic regime both optimisers track the reference
     probs = ctx.forward_rows(row0=0, bs=64)
     want_p = g[f"{opt}_probs_first64"]
     if (mode, opt) == ("fp32", "sgd"):
@@ -402,6 +403,51 @@ def test_streamed_image_step_equals_resident_step(lib, ctx):
     assert abs(results[0][0][0] - results[1][0][0]) < 1e-6 * abs(results[0][0][0])
     for a, bb in zip(results[0][1], results[1][1]):
         np.testing.assert_allclose(a, bb, rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("memory", ["pinned", "pageable"])
+def test_streaming_epoch_equals_resident_epoch(lib, ctx, memory):
+    """train_epoch_images (copy stream || compute stream, sequential / permuted rows, short last batch)
+    == dataset_extract + train_epoch on the same permutation."""
+    import torch
+    S, C, layers, n, bs = 32, 10, [64, 32], 1000, 256          # 256,256,256,232
+    imgs, lab = synth_images(n, S, 11), synth_labels(n, C, 12).astype(np.int32)
+    if memory == "pinned":
+        t_img = torch.empty(imgs.shape, dtype=torch.uint8, pin_memory=True)
+        t_lab = torch.empty(lab.shape, dtype=torch.int32, pin_memory=True)
+        t_img.numpy()[:] = imgs
+        t_lab.numpy()[:] = lab
+        img_ptr, lab_ptr = t_img.data_ptr(), t_lab.data_ptr()
+    else:
+        img_ptr, lab_ptr = imgs.ctypes.data, lab.ctypes.data
+    perm = np.random.default_rng(3).permutation(n)
+
+    def fresh():
+        ctx.set_math_mode(lib.MATH_FP32_SIMT)
+        ctx.set_filters(O.DEFAULT_FILTERS)
+        D = ctx.feature_count(S)
+        ctx.set_network(D, layers, C)
+        w, b = O.init_layers(D, layers, C, seed=42)
+        wk, bk = O.layer_keys(len(layers))
+        for l, (wn, bn) in enumerate(zip(wk, bk)):
+            ctx.set_param(2 * l, w[wn])
+            ctx.set_param(2 * l + 1, b[bn])
+        ctx.set_optimizer(lib.OPT_ADAM, 1e-3)
+
+    for p in (None, perm):
+        fresh()
+        ctx.dataset_alloc(n)
+        ctx.dataset_extract(0, imgs)
+        ctx.dataset_set_labels(0, lab)
+        want = ctx.train_epoch(np.arange(n) if p is None else p, bs)
+        want_params = [ctx.get_param(i) for i in range(ctx.num_params())]
+        fresh()
+        loss, correct, steps = ctx.train_epoch_images(img_ptr, lab_ptr, n, S, bs, perm=p, want_step_stats=True)
+        assert correct == want[1] and abs(loss - want[0]) < 1e-9 * abs(want[0])
+        assert steps.shape == (4, 2) and abs(steps[-1, 0] - loss) < 1e-9 * abs(loss) and np.all(np.diff(steps[:, 0]) > 0)
+        # same arithmetic, but bias-gradient partial sums meet in float atomics: equal to rounding, not bitwise
+        for a, bb in zip(want_params, [ctx.get_param(i) for i in range(ctx.num_params())]):
+            assert rel_err(bb, a) < 1e-5
 
 
 def test_predict_and_evaluate_images(lib, ctx):
