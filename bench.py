@@ -51,47 +51,72 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md).  NVML is polled in-process
+    (nvidia_ml_py) from a thread, initialised before the warm-up: spawning `nvidia-smi -lms` next to a
+    10 ms timed region perturbs it (its NVML start-up stalled some runs by 3x); nvidia-smi is the fallback."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, period=0.05):
+        self.rows, self.stop_flag, self.nvml, self.proc = [], False, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.period = period
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.nvml = None
+            self._start_smi(index)
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((time.time(), sm, rs, pw))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def _start_smi(self, index):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0=None, t1=None):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for (t, r) in self.rows if (t0 is None or t0 - 0.05 <= t <= t1 + 0.15)] or [r for _, r in self.rows]
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            parts = [x.strip() for x in r.split(",")]
+            parts = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-                power.append(float(parts[2]))
-                for nm, v in zip(names, parts[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                rs = sum(bit for (nm, bit), v in zip(self.REASONS.items(), parts[3:7]) if v.lower().startswith("active"))
+                self.max_sm = float(parts[1])
+                self.rows.append((time.time(), float(parts[0]), rs, float(parts[2])))
             except Exception:
                 continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self, t0=None, t1=None):
+        self.stop_flag = True
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        rows = [r for r in self.rows if (t0 is None or t0 <= r[0] <= t1)] or self.rows
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        reasons = sorted(nm for nm, bit in self.REASONS.items() if any(r[2] & bit for r in rows))
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(self.max_sm),
+                "power_w_max": max(r[3] for r in rows), "samples": len(rows), "reasons": reasons,
+                "source": "nvml in-process" if self.nvml else "nvidia-smi"}
 
 
 def synth_model(lib, device):
@@ -124,6 +149,7 @@ def run_ours(args):
         uid = parallel.broadcast_bytes(lib.comm_unique_id() if rank == 0 else None)
         ctx.comm_init(uid, rank, world)
 
+    sampler = ClockSampler(local) if rank == 0 else None      # NVML up and polling well before the timed regions
     # ---------------- resident dataset: extract N_RESIDENT synthetic images on the device
     rng = np.random.default_rng(1000 + rank)
     ctx.dataset_alloc(N_RESIDENT)
@@ -143,8 +169,7 @@ def run_ours(args):
             torch.distributed.barrier()
         ctx.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None      # samples from warm-up to the end of the e2e loop
-    t_load0 = time.time()
+    t_load0 = time.time()                                      # clock samples: warm-up .. end of the e2e loops
     if W:
         ctx.train_epoch(warm_idx, gbs)
     barrier()

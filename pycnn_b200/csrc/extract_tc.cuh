@@ -15,13 +15,16 @@
 // are exact in fp32 and the /255 of pycnn.py:273 is applied once, in fp32, in the epilogue.  The result
 // is at least as close to the float64 reference as the FP32 SIMT kernel.
 //
-// Persistent, warp-specialised (320 threads):
-//   warp 0      producer : cp.async.bulk (TMA 1-D) of the contiguous byte span of input rows a tile needs
-//   warps 1-4   builders : raw u8 HWC -> channel sums (dp4a) -> fp16 patch rows -> A tile in smem
-//                          (canonical K-major no-swizzle core-matrix layout), fence.proxy.async
-//   warp 5      MMA      : tcgen05.mma hi (+ lo) into a double-buffered TMEM accumulator, tcgen05.commit
-//   warps 6-9   epilogue : tcgen05.ld 16 columns = 4 filters x 4 quadrants -> max4 -> ReLU -> scale ->
-//                          coalesced stores straight into the filter-major feature row
+// Persistent kernel, one CTA per SM, up to four 128-thread warpgroups per CTA; every warpgroup owns whole
+// 128-position tiles end to end, so no warp idles polling on another role's barrier:
+//   prefetch : one elected thread issues cp.async.bulk (TMA 1-D) for the contiguous byte span of input rows
+//              the warpgroup's NEXT tile needs (double-buffered, mbarrier expect_tx);
+//   build    : thread m turns raw u8 HWC bytes into the fp16 patch row m (dp4a channel sums, magic-number
+//              int->fp16) in the canonical K-major no-swizzle core-matrix layout; fence.proxy.async; bar.sync;
+//   MMA      : the elected thread issues tcgen05.mma hi (+ lo) into the warpgroup's TMEM accumulator and
+//              tcgen05.commit's to an mbarrier; other warpgroups of the SM are building / storing meanwhile;
+//   epilogue : tcgen05.ld 16 columns = 4 filters x 4 quadrants -> max4 -> ReLU -> scale -> coalesced stores
+//              straight into the filter-major feature row.
 // Output rows are written exactly once; input bytes are read exactly once (plus tile-edge halos).
 #pragma once
 #include <cuda_fp16.h>
@@ -32,12 +35,11 @@
 namespace pb {
 namespace tcx {
 
-constexpr int RAW_BYTES = 24 * 1024;
-constexpr int RAW_STAGES = 3;
-constexpr int A_BYTES = 128 * 32;  // 128 rows x 16 fp16
-constexpr int A_STAGES = 4;
-constexpr int MAX_F = 64;          // 4*F <= 256 accumulator columns per stage
-constexpr int THREADS = 320;
+constexpr int RAW_BYTES_MAX = 24 * 1024;   // largest staged span supported (bounds S)
+constexpr int A_BYTES = 128 * 32;          // 128 rows x 16 fp16
+constexpr int MAX_F = 64;                  // 4*F <= 256 accumulator columns
+constexpr int MAX_WG = 4;                  // warpgroups per CTA (TMEM: MAX_WG * columns <= 512)
+constexpr int MAX_SLOTS = 6;               // raw staging ring depth per warpgroup (HBM latency >> per-tile work)
 constexpr int B_BYTES_MAX = 256 * 32;
 
 struct FastDiv {   // n / d for n < 2^31 by multiply-high: q = umulhi(n, mul) >> shift   (d == 1: mul == 0)
@@ -66,8 +68,12 @@ struct ExArgs {
   FastDiv div_pp, div_pw;
   int F, N;       // N = 4 * round_up(F, 4) accumulator columns
   int has_lo;
-  int stage_cols; // TMEM columns per accumulator stage (tmem_cols / 2)
-  int tmem_cols;
+  int nwg;        // warpgroups per CTA
+  int raw_bytes;  // bytes per raw staging slot (multiple of 128)
+  int nslots;     // raw staging slots per warpgroup = prefetch distance + 1 (2..MAX_SLOTS)
+  int wg_cols;    // TMEM columns per warpgroup accumulator
+  int tmem_cols;  // total allocation (power of two)
+  int debug;      // PYCNN_B200_EXTRACT_DEBUG bit0: no global stores, bit1: no patch build, bit2: no MMA/epilogue math
   const uint8_t* bpack;  // [hi | lo], each N x 16 fp16 in canonical core-matrix order
   const float* scale;    // per filter: 2^e / 255
 };
@@ -102,176 +108,162 @@ __device__ __forceinline__ uint32_t pack_sums_to_half2(uint32_t s_lo, uint32_t s
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(THREADS, 2) extract_tc_kernel(const __grid_constant__ ExArgs a) {
-  extern __shared__ uint8_t smem_raw_[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_) + 127) & ~uintptr_t(127));
-  uint8_t* raw = smem;                                      // RAW_STAGES x RAW_BYTES
-  uint8_t* a_ring = raw + RAW_STAGES * RAW_BYTES;           // A_STAGES x A_BYTES
-  uint8_t* b_hi = a_ring + A_STAGES * A_BYTES;              // N x 32 B
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(128 * MAX_WG, 1) extract_tc_kernel(const __grid_constant__ ExArgs a) {
+  // declared with its alignment so that every pointer derived from it stays in the shared address space
+  // (a manual (addr+127)&~127 fix-up degrades all accesses to generic LD/ST)
+  extern __shared__ __align__(128) uint8_t smem[];
+  // layout: [B hi][B lo][scale][barriers + span info][per warpgroup: raw slot 0, raw slot 1, A tile]
+  uint8_t* b_hi = smem;
   uint8_t* b_lo = b_hi + B_BYTES_MAX;
-  float* s_scale = reinterpret_cast<float*>(b_lo + B_BYTES_MAX);  // MAX_F floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_scale + MAX_F);
-  uint64_t* raw_full = bars;                 // [RAW_STAGES]
-  uint64_t* raw_empty = raw_full + RAW_STAGES;
-  uint64_t* a_full = raw_empty + RAW_STAGES; // [A_STAGES]
-  uint64_t* a_empty = a_full + A_STAGES;
-  uint64_t* tmem_full = a_empty + A_STAGES;  // [2]
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint2* span_info = reinterpret_cast<uint2*>(tmem_slot + 2);     // [RAW_STAGES] {g0, shift} of the staged span
+  float* s_scale = reinterpret_cast<float*>(b_lo + B_BYTES_MAX);   // MAX_F floats
+  constexpr int BPW = MAX_SLOTS + 1;                                  // barriers per warpgroup
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_scale + MAX_F);      // per wg: raw_full[MAX_SLOTS], mma_done
+  uint2* span_info = reinterpret_cast<uint2*>(bars + BPW * MAX_WG);   // per wg: [MAX_SLOTS] {g0, shift}
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(span_info + MAX_SLOTS * MAX_WG);
+  uint8_t* wg_base = reinterpret_cast<uint8_t*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wg = warp >> 2, m = threadIdx.x & 127;
+  const int NS = a.nslots;
+  uint64_t* raw_full = bars + BPW * wg;
+  uint64_t* mma_done = raw_full + MAX_SLOTS;
+  uint2* my_span = span_info + MAX_SLOTS * wg;
+  uint8_t* raw = wg_base + (size_t)wg * (NS * a.raw_bytes + A_BYTES);
+  uint8_t* a_tile = raw + NS * a.raw_bytes;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < RAW_STAGES; ++s) { tc::mbar_init(&raw_full[s], 1); tc::mbar_init(&raw_empty[s], 128); }
-    for (int s = 0; s < A_STAGES; ++s) { tc::mbar_init(&a_full[s], 128); tc::mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], 128); }
+    for (int i = 0; i < a.nwg * BPW; ++i) tc::mbar_init(&bars[i], 1);
     tc::fence_barrier_init();
   }
-  if (warp == 5) tc::tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  if (warp == 0) tc::tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   {  // filter operand + scales: global -> smem (generic proxy), made visible to the tensor core below
     const int b_bytes = a.N * 32;
     const uint4* src = reinterpret_cast<const uint4*>(a.bpack);
-    for (int i = threadIdx.x; i < b_bytes / 16; i += THREADS) {
+    for (int i = threadIdx.x; i < b_bytes / 16; i += blockDim.x) {
       reinterpret_cast<uint4*>(b_hi)[i] = src[i];
       reinterpret_cast<uint4*>(b_lo)[i] = src[b_bytes / 16 + i];
     }
-    for (int i = threadIdx.x; i < a.F; i += THREADS) s_scale[i] = a.scale[i];
+    for (int i = threadIdx.x; i < MAX_F; i += blockDim.x) s_scale[i] = (i < a.F) ? a.scale[i] : 0.f;
   }
   tc::fence_proxy_async_smem();
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
-  const uint32_t tmem_base = *tmem_slot;
-  const int tile_step = gridDim.x;
+  const uint32_t tmem_acc = *tmem_slot + (uint32_t)(wg * a.wg_cols);
+  const uint32_t lane_taddr = tmem_acc + (static_cast<uint32_t>((warp & 3) * 32) << 16);
 
-  if (warp == 0) {
-    // ===== producer: one bulk copy per tile; publishes {g0, shift} of the span next to the data =====
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 1;   // parity to wait for on raw_empty: first pass falls through
-      for (int t = blockIdx.x; t < a.num_tiles; t += tile_step) {
-        tc::mbar_wait(&raw_empty[s], ph);
-        const Span sp = tile_span(a, t);
-        span_info[s] = make_uint2(sp.g0, sp.shift);
-        tc::mbar_arrive_expect_tx(&raw_full[s], sp.bytes);     // release: span_info is visible to waiters
-        tc::bulk_load(raw + s * RAW_BYTES, a.images + sp.b0, sp.bytes, &raw_full[s]);
-        if (++s == RAW_STAGES) { s = 0; ph ^= 1; }
+  const int tile0 = blockIdx.x * a.nwg + wg;
+  const int tile_step = gridDim.x * a.nwg;
+  const uint32_t SS = (uint32_t)a.S * a.S, S3 = 3u * a.S;
+  const uint32_t idesc = tc::make_idesc(tc::FMT_F16, 128, a.N, false, false);
+  const uint64_t dbh = tc::make_smem_desc(tc::smem_u32(b_hi), 128, 256, tc::UMMA_SWIZZLE_NONE);
+  const uint64_t dbl = tc::make_smem_desc(tc::smem_u32(b_lo), 128, 256, tc::UMMA_SWIZZLE_NONE);
+  const uint64_t da = tc::make_smem_desc(tc::smem_u32(a_tile), 128, 256, tc::UMMA_SWIZZLE_NONE);
+  uint8_t* const arow = a_tile + (m >> 3) * 256 + (m & 7) * 16;
+  const int nchunks = a.N >> 4;
+  const int bar_id = 1 + wg;
+
+  if (m == 0) {   // fill the ring: the first NS-1 tiles of this warpgroup
+    for (int j = 0; j < NS - 1; ++j) {
+      const int tj = tile0 + j * tile_step;
+      if (tj >= a.num_tiles) break;
+      const Span sp = tile_span(a, tj);
+      my_span[j] = make_uint2(sp.g0, sp.shift);
+      tc::mbar_arrive_expect_tx(&raw_full[j], sp.bytes);
+      tc::bulk_load(raw + j * a.raw_bytes, a.images + sp.b0, sp.bytes, &raw_full[j]);
+    }
+  }
+  int it = 0, s = 0;           // s = it % NS
+  uint32_t ph = 0;             // (it / NS) & 1
+  for (int t = tile0; t < a.num_tiles; t += tile_step, ++it) {
+    // ---- prefetch tile it+NS-1 into the slot tile it-1 used (everyone finished reading it before the last bar.sync)
+    if (m == 0) {
+      const int tn = t + (NS - 1) * tile_step;
+      if (tn < a.num_tiles) {
+        const int sn = (s == 0) ? NS - 1 : s - 1;
+        const Span sp = tile_span(a, tn);
+        my_span[sn] = make_uint2(sp.g0, sp.shift);
+        tc::mbar_arrive_expect_tx(&raw_full[sn], sp.bytes);
+        tc::bulk_load(raw + sn * a.raw_bytes, a.images + sp.b0, sp.bytes, &raw_full[sn]);
       }
     }
-  } else if (warp <= 4) {
-    // ===== builders: thread m builds row m of the A tile =====
-    const int m = threadIdx.x - 32;
-    int sr = 0, sa = 0;
-    uint32_t ph_r = 0, ph_a = 1;
-    const uint32_t SS = (uint32_t)a.S * a.S, S3 = 3u * a.S;
-    uint8_t* const arow0 = a_ring + (m >> 3) * 256 + (m & 7) * 16;
-    for (int t = blockIdx.x; t < a.num_tiles; t += tile_step) {
-      const uint32_t r = (uint32_t)t * 128u + m;
-      uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      uint32_t pix = 0;
-      const bool valid = r < (uint32_t)a.R;
-      if (valid) {   // position decode overlaps the wait for the raw bytes
-        const uint32_t img = fdiv(r, a.div_pp), p = r - img * a.PP, py = fdiv(p, a.div_pw), px = p - py * a.PW;
-        pix = img * SS + 2u * py * a.S + 2u * px;
-      }
-      tc::mbar_wait(&raw_full[sr], ph_r);
-      if (valid) {
-        const uint2 info = span_info[sr];
-        const uint32_t* words = reinterpret_cast<const uint32_t*>(raw + sr * RAW_BYTES);
-        uint32_t off = info.y + 3u * (pix - info.x);
+    // ---- build: thread m -> row m of the A tile
+    const uint32_t r = (uint32_t)t * 128u + m;
+    const bool valid = r < (uint32_t)a.R;
+    uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t pix = 0, img = 0, p = 0;
+    if (valid) {   // position decode overlaps the wait for the raw bytes
+      img = fdiv(r, a.div_pp);
+      p = r - img * a.PP;
+      const uint32_t py = fdiv(p, a.div_pw), px = p - py * a.PW;
+      pix = img * SS + 2u * py * a.S + 2u * px;
+    }
+    tc::mbar_wait(&raw_full[s], ph);
+    if (valid && !(a.debug & 2)) {
+      const uint2 info = my_span[s];
+      const uint32_t* words = reinterpret_cast<const uint32_t*>(raw + s * a.raw_bytes);
+      uint32_t off = info.y + 3u * (pix - info.x);
 #pragma unroll
-        for (int u = 0; u < 4; ++u, off += S3) {
-          const uint32_t w = off >> 2, sh = (off & 3u) * 8u;
-          const uint32_t x0 = words[w], x1 = words[w + 1], x2 = words[w + 2], x3 = words[w + 3];
-          const uint32_t W0 = __funnelshift_r(x0, x1, sh), W1 = __funnelshift_r(x1, x2, sh),
-                         W2 = __funnelshift_r(x2, x3, sh);
-          // bytes: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
-          const uint32_t s0 = __dp4a(W0, 0x00010101u, 0u);
-          const uint32_t s1 = __dp4a(W0, 0x01000000u, __dp4a(W1, 0x00000101u, 0u));
-          const uint32_t s2 = __dp4a(W1, 0x01010000u, __dp4a(W2, 0x00000001u, 0u));
-          const uint32_t s3 = __dp4a(W2, 0x01010100u, 0u);
-          h[2 * u] = pack_sums_to_half2(s0, s1);
-          h[2 * u + 1] = pack_sums_to_half2(s2, s3);
-        }
-      }
-      tc::mbar_wait(&a_empty[sa], ph_a);
-      uint8_t* arow = arow0 + sa * A_BYTES;
-      *reinterpret_cast<uint4*>(arow) = make_uint4(h[0], h[1], h[2], h[3]);        // k = 0..7  (u = 0,1)
-      *reinterpret_cast<uint4*>(arow + 128) = make_uint4(h[4], h[5], h[6], h[7]);  // k = 8..15 (u = 2,3)
-      tc::fence_proxy_async_smem();
-      tc::mbar_arrive(&a_full[sa]);
-      tc::mbar_arrive(&raw_empty[sr]);
-      if (++sr == RAW_STAGES) { sr = 0; ph_r ^= 1; }
-      if (++sa == A_STAGES) { sa = 0; ph_a ^= 1; }
-    }
-  } else if (warp == 5) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc(tc::FMT_F16, 128, a.N, false, false);
-      const uint64_t dbh = tc::make_smem_desc(tc::smem_u32(b_hi), 128, 256, tc::UMMA_SWIZZLE_NONE);
-      const uint64_t dbl = tc::make_smem_desc(tc::smem_u32(b_lo), 128, 256, tc::UMMA_SWIZZLE_NONE);
-      const uint64_t da0 = tc::make_smem_desc(tc::smem_u32(a_ring), 128, 256, tc::UMMA_SWIZZLE_NONE);
-      int sa = 0, acc = 0;
-      uint32_t ph_a = 0, ph_t = 1;
-      for (int t = blockIdx.x; t < a.num_tiles; t += tile_step) {
-        tc::mbar_wait(&tmem_empty[acc], ph_t);
-        tc::mbar_wait(&a_full[sa], ph_a);
-        tc::fence_after_thread_sync();
-        const uint64_t da = da0 + (uint64_t)((sa * A_BYTES) >> 4);   // start-address field is in 16-byte units
-        const uint32_t d = tmem_base + (uint32_t)(acc * a.stage_cols);
-        tc::mma_f16(d, da, dbh, idesc, 0u);
-        if (a.has_lo) tc::mma_f16(d, da, dbl, idesc, 1u);
-        tc::mma_commit(&a_empty[sa]);
-        tc::mma_commit(&tmem_full[acc]);
-        if (++sa == A_STAGES) { sa = 0; ph_a ^= 1; }
-        if (++acc == 2) { acc = 0; ph_t ^= 1; }
+      for (int u = 0; u < 4; ++u, off += S3) {
+        const uint32_t w = off >> 2, sh = (off & 3u) * 8u;
+        const uint32_t x0 = words[w], x1 = words[w + 1], x2 = words[w + 2], x3 = words[w + 3];
+        const uint32_t W0 = __funnelshift_r(x0, x1, sh), W1 = __funnelshift_r(x1, x2, sh),
+                       W2 = __funnelshift_r(x2, x3, sh);
+        // bytes: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+        const uint32_t s0 = __dp4a(W0, 0x00010101u, 0u);
+        const uint32_t s1 = __dp4a(W0, 0x01000000u, __dp4a(W1, 0x00000101u, 0u));
+        const uint32_t s2 = __dp4a(W1, 0x01010000u, __dp4a(W2, 0x00000001u, 0u));
+        const uint32_t s3 = __dp4a(W2, 0x01010100u, 0u);
+        h[2 * u] = pack_sums_to_half2(s0, s1);
+        h[2 * u + 1] = pack_sums_to_half2(s2, s3);
       }
     }
-  } else {
-    // ===== epilogue (warps 6..9): TMEM lane quarter = warp % 4 =====
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    int acc = 0;
-    uint32_t ph_t = 0;
-    const int nchunks = a.N >> 4;
-    for (int t = blockIdx.x; t < a.num_tiles; t += tile_step) {
-      const uint32_t r = (uint32_t)t * 128u + m;
-      const bool valid = r < (uint32_t)a.R;
-      const uint32_t img = valid ? fdiv(r, a.div_pp) : 0u, p = valid ? r - img * a.PP : 0u;
-      float* o = a.out + (int64_t)img * a.ld + p;
-      tc::mbar_wait(&tmem_full[acc], ph_t);
+    *reinterpret_cast<uint4*>(arow) = make_uint4(h[0], h[1], h[2], h[3]);        // k = 0..7  (u = 0,1)
+    *reinterpret_cast<uint4*>(arow + 128) = make_uint4(h[4], h[5], h[6], h[7]);  // k = 8..15 (u = 2,3)
+    tc::fence_proxy_async_smem();       // A rows visible to the tensor core (async proxy)
+    tc::fence_before_thread_sync();     // orders the previous tile's tcgen05.ld before the next MMA
+    named_bar_sync(bar_id, 128);
+    // ---- MMA: one thread for the warpgroup
+    if (m == 0) {
       tc::fence_after_thread_sync();
-      const uint32_t taddr = lane_base + (uint32_t)(acc * a.stage_cols);
-      int f = 0;
-#pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        float v[16];
-        __syncwarp();
-        tc::tmem_ld16(taddr + c * 16, v);
-#pragma unroll
-        for (int j = 0; j < 4; ++j, ++f, o += a.PP) {
-          float mx = fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3]));
-          mx = fmaxf(mx, 0.f) * s_scale[f];      // s_scale is padded to MAX_F: no bound check on the load
-          if (valid && f < a.F) *o = mx;
-        }
-      }
-      __syncwarp();
-      tc::fence_before_thread_sync();
-      tc::mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; ph_t ^= 1; }
+      tc::mma_f16(tmem_acc, da, dbh, idesc, 0u);
+      if (a.has_lo) tc::mma_f16(tmem_acc, da, dbl, idesc, 1u);
+      tc::mma_commit(mma_done);
     }
+    __syncwarp();
+    // ---- epilogue: thread m owns pooled position r; lanes of a warp = consecutive positions
+    float* o = a.out + (int64_t)img * a.ld + p;
+    tc::mbar_wait(mma_done, it & 1);
+    tc::fence_after_thread_sync();
+    int f = 0;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      float v[16];
+      __syncwarp();
+      tc::tmem_ld16(lane_taddr + c * 16, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j, ++f, o += a.PP) {
+        float mx = fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3]));
+        mx = fmaxf(mx, 0.f) * s_scale[f];
+        if (valid && f < a.F && !(a.debug & 1)) *o = mx;
+      }
+    }
+    if (++s == NS) { s = 0; ph ^= 1; }
   }
   tc::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 0) {
     tc::fence_after_thread_sync();
-    tc::tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    tc::tmem_dealloc(*tmem_slot, (uint32_t)a.tmem_cols);
   }
 }
 
-constexpr int SMEM_BYTES = RAW_STAGES * RAW_BYTES + A_STAGES * A_BYTES + 2 * B_BYTES_MAX + MAX_F * 4 + 320 + 128;
+constexpr int SMEM_FIXED = 2 * B_BYTES_MAX + MAX_F * 4 + (MAX_SLOTS + 1) * MAX_WG * 8 + MAX_SLOTS * MAX_WG * 8 + 16 + 256;
+
 
 }  // namespace tcx
 
@@ -297,7 +289,7 @@ static inline int64_t tc_extract_max_span(int S) {
 
 static inline bool tc_extract_supported(const pycnn_b200_ctx* c, int S) {
   return c->F > 0 && c->F <= tcx::MAX_F && c->d_tc_filters != nullptr && S >= 4 &&
-         tc_extract_max_span(S) <= tcx::RAW_BYTES - 32;
+         tc_extract_max_span(S) <= tcx::RAW_BYTES_MAX - 32;
 }
 
 // Pack flip(k) into the per-quadrant B operand (hi and lo fp16 parts), canonical K-major no-swizzle
@@ -346,7 +338,7 @@ static inline int tc_extract_set_filters(pycnn_b200_ctx* c) {
 }
 
 static inline int tc_extract_prepare(pycnn_b200_ctx*) {
-  PB_CUDA(cudaFuncSetAttribute(tcx::extract_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcx::SMEM_BYTES));
+  PB_CUDA(cudaFuncSetAttribute(tcx::extract_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   return 0;
 }
 
@@ -354,8 +346,17 @@ static inline int tc_extract(pycnn_b200_ctx* c, const uint8_t* d_images, int64_t
   const int PW = (S - 2) / 2, PP = PW * PW;
   const int N = std::abs(c->tc_ncols);
   PB_CHECK(N > 0 && PP > 0, "tensor-core extractor not configured");
-  int tmem_cols = 32;
-  while (tmem_cols < 2 * N) tmem_cols <<= 1;
+  int wg_cols = 32;
+  while (wg_cols < N) wg_cols <<= 1;                       // accumulator columns per warpgroup (power of two)
+  const int nwg = std::min(tcx::MAX_WG, 512 / wg_cols);    // TMEM has 512 columns per SM
+  const int tmem_cols = nwg * wg_cols;                     // 128..512, a power of two
+  const int raw_bytes = (int)round_up(tc_extract_max_span(S) + 32, 128);
+  // ring depth: as deep as shared memory allows (HBM latency is several tiles' worth of work), 2..MAX_SLOTS
+  const int64_t budget = 216 * 1024 - tcx::SMEM_FIXED - 128;
+  int nslots = (int)((budget / nwg - tcx::A_BYTES) / raw_bytes);
+  nslots = std::max(2, std::min(nslots, tcx::MAX_SLOTS));
+  const size_t smem_bytes = tcx::SMEM_FIXED + (size_t)nwg * ((size_t)nslots * raw_bytes + tcx::A_BYTES) + 128;
+  PB_CHECK(smem_bytes <= 220 * 1024, "tensor-core extractor: staging does not fit in shared memory");
   // keep all device-side index arithmetic in 32 bits: bound rows and bytes per launch
   int64_t per_launch = std::max<int64_t>(1, std::min<int64_t>((1ll << 30) / PP, (1ll << 30) / ((int64_t)3 * S * S)));
   if (per_launch >= 16) per_launch = per_launch / 16 * 16;   // keeps every launch's image base 16-byte aligned
@@ -370,16 +371,16 @@ static inline int tc_extract(pycnn_b200_ctx* c, const uint8_t* d_images, int64_t
     a.S = S; a.PW = PW; a.PP = PP;
     a.div_pp = tcx::make_fastdiv((uint32_t)PP); a.div_pw = tcx::make_fastdiv((uint32_t)PW);
     a.F = c->F; a.N = N; a.has_lo = c->tc_ncols > 0 ? 1 : 0;
-    a.tmem_cols = tmem_cols; a.stage_cols = tmem_cols / 2;
+    a.nwg = nwg; a.raw_bytes = raw_bytes; a.nslots = nslots; a.wg_cols = wg_cols; a.tmem_cols = tmem_cols;
+    { const char* dbg = getenv("PYCNN_B200_EXTRACT_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
     a.bpack = static_cast<const uint8_t*>(c->d_tc_filters);
     a.scale = c->d_tc_scale;
     // the image base must be 16-byte aligned for the bulk copies (cudaMalloc gives 256; chunk offsets keep 16
     // when 3*S*S*i0 is a multiple of 16 -- per_launch is rounded to make it so)
     PB_CHECK((reinterpret_cast<uintptr_t>(a.images) & 15) == 0, "image batch is not 16-byte aligned");
-    const int ctas_per_sm = tmem_cols <= 256 ? 2 : 1;
-    const int grid = std::min(a.num_tiles, ctas_per_sm * c->num_sms);
+    const int grid = (int)std::min<int64_t>(ceil_div(a.num_tiles, nwg), c->num_sms);
     LaunchScope ls(c, KC_EXTRACT);
-    tcx::extract_tc_kernel<<<grid, tcx::THREADS, tcx::SMEM_BYTES, c->stream>>>(a);
+    tcx::extract_tc_kernel<<<grid, 128 * nwg, smem_bytes, c->stream>>>(a);
     PB_CUDA(cudaGetLastError());
   }
   return 0;

@@ -68,6 +68,27 @@ def extract_timing(ctx):
             print(f"extract timing {mname}: ERROR {e}", flush=True)
 
 
+def extract_ablate(ctx):
+    """Where does the tensor-core extractor's time go?  Debug switches knock out one stage at a time."""
+    ctx.set_filters(O.DEFAULT_FILTERS)
+    ctx.set_network(4275, [8], 2)
+    n = 65536
+    imgs = synth_images(n, 32, seed=0)
+    ctx.dataset_alloc(n)
+    ctx.set_extract_mode(lib.EXTRACT_TC)
+    for dbg, what in ((0, "full"), (1, "no global stores"), (2, "no patch build"), (3, "no stores, no build")):
+        os.environ["PYCNN_B200_EXTRACT_DEBUG"] = str(dbg)
+        ctx.dataset_extract(0, imgs)
+        ctx.set_kernel_timing(True)
+        ctx.kernel_stats(reset=True)
+        for _ in range(5):
+            ctx.dataset_extract(0, imgs)
+        st = ctx.kernel_stats(reset=True)["extract_conv_relu_pool"]
+        ctx.set_kernel_timing(False)
+        print(f"extract ablation [{what}]: {st[1] / st[0]:.4f} ms / {n} imgs", flush=True)
+    os.environ["PYCNN_B200_EXTRACT_DEBUG"] = "0"
+
+
 def gemm_timing(ctx):
     ctx.set_math_mode(lib.MATH_TF32)
     for (M, N, K, ak, bk, name) in [(4096, 256, 4275, 1, 1, "fwd1"), (256, 4275, 4096, 0, 0, "dW1"),
@@ -88,7 +109,8 @@ if __name__ == "__main__":
     for w in what:
         ctx = lib.Context(0)
         try:
-            {"gemm": gemm_diag, "extract": extract_diag, "extract_timing": extract_timing, "gemm_timing": gemm_timing}[w](ctx)
+            {"gemm": gemm_diag, "extract": extract_diag, "extract_timing": extract_timing, "gemm_timing": gemm_timing,
+             "extract_ablate": extract_ablate}[w](ctx)
         except Exception as e:
             print(f"{w}: FATAL {e}", flush=True)
         try:
