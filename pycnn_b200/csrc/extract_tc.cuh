@@ -167,7 +167,9 @@ __global__ void __launch_bounds__(128 * MAX_WG, 1) extract_tc_kernel(const __gri
   const int nchunks = a.N >> 4;
   const int bar_id = 1 + wg;
 
-  if (m == 0) {   // fill the ring: the first NS-1 tiles of this warpgroup
+  // the prefetch thread (warp 1 of the warpgroup) and the MMA thread (warp 0) are different warps on purpose:
+  // the extra scalar work is spread instead of making one warp the straggler at every bar.sync
+  if (m == 32) {   // fill the ring: the first NS-1 tiles of this warpgroup
     for (int j = 0; j < NS - 1; ++j) {
       const int tj = tile0 + j * tile_step;
       if (tj >= a.num_tiles) break;
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(128 * MAX_WG, 1) extract_tc_kernel(const __gri
   uint32_t ph = 0;             // (it / NS) & 1
   for (int t = tile0; t < a.num_tiles; t += tile_step, ++it) {
     // ---- prefetch tile it+NS-1 into the slot tile it-1 used (everyone finished reading it before the last bar.sync)
-    if (m == 0) {
+    if (m == 32) {
       const int tn = t + (NS - 1) * tile_step;
       if (tn < a.num_tiles) {
         const int sn = (s == 0) ? NS - 1 : s - 1;
@@ -239,17 +241,31 @@ __global__ void __launch_bounds__(128 * MAX_WG, 1) extract_tc_kernel(const __gri
     float* o = a.out + (int64_t)img * a.ld + p;
     tc::mbar_wait(mma_done, it & 1);
     tc::fence_after_thread_sync();
-    int f = 0;
+    // 16 accumulator columns per tcgen05.ld = 4 filters x 4 pool quadrants.  Per filter: two 3-input max
+    // (FMNMX3: quadrant max, then ReLU folded in), one FMUL by the per-filter scale (one LDS.128 per chunk),
+    // one store.  All chunks but the last hold four real filters, so only the last one checks f < F.
+    const int full_chunks = a.F >> 2;
+    const bool st_ok = valid && !(a.debug & 1);
 #pragma unroll 1
-    for (int c = 0; c < nchunks; ++c) {
+    for (int c = 0; c < full_chunks; ++c) {
       float v[16];
-      __syncwarp();
       tc::tmem_ld16(lane_taddr + c * 16, v);
+      const float4 sc = *reinterpret_cast<const float4*>(s_scale + 4 * c);
+      const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j, ++f, o += a.PP) {
-        float mx = fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3]));
-        mx = fmaxf(mx, 0.f) * s_scale[f];
-        if (valid && f < a.F && !(a.debug & 1)) *o = mx;
+      for (int j = 0; j < 4; ++j, o += a.PP) {
+        const float mx = fmaxf(fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), v[4 * j + 2]), fmaxf(v[4 * j + 3], 0.f));
+        if (st_ok) *o = mx * scv[j];
+      }
+    }
+    if (full_chunks < nchunks) {   // ragged last chunk (F % 4 filters)
+      float v[16];
+      tc::tmem_ld16(lane_taddr + full_chunks * 16, v);
+      const int rem = a.F & 3;
+#pragma unroll
+      for (int j = 0; j < 3; ++j, o += a.PP) {
+        const float mx = fmaxf(fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), v[4 * j + 2]), fmaxf(v[4 * j + 3], 0.f));
+        if (st_ok && j < rem) *o = mx * s_scale[4 * full_chunks + j];
       }
     }
     if (++s == NS) { s = 0; ph ^= 1; }
