@@ -145,9 +145,13 @@ def run_ours(args):
     if world > 1:
         parallel.init_process_group("nccl")
     ctx = synth_model(lib, local)
+    dp_mode = "single"
     if world > 1:
         uid = parallel.broadcast_bytes(lib.comm_unique_id() if rank == 0 else None)
         ctx.comm_init(uid, rank, world)
+        dp_mode = os.environ.get("PYCNN_B200_DP", "p2p" if world <= 8 else "nccl")
+        if dp_mode == "p2p":      # fused reduce-scatter -> norm -> sharded Adam -> all-gather over NVLink peer memory
+            parallel.attach_peer_memory(ctx, rank, world)
 
     sampler = ClockSampler(local) if rank == 0 else None      # NVML up and polling well before the timed regions
     # ---------------- resident dataset: extract N_RESIDENT synthetic images on the device
@@ -275,6 +279,8 @@ def run_ours(args):
                                "batch 4096 per GPU, CPU update rule (clip 5, frozen t)",
                    "global_batch": gbs, "resident_rows": N_RESIDENT, "feature_dim": D,
                    "parallelism": f"dp{world}" if world > 1 else "single",
+                   "gradient_exchange": {"single": "none", "p2p": "fused peer-memory reduce-scatter/update/all-gather (NVLink, CUDA IPC)",
+                                         "nccl": "ncclAllReduce(sum) of the flat gradient + replicated update"}[dp_mode],
                    "l2": "inputs larger than L2: 1.1 GB resident fp32 feature matrix, fresh random rows every step",
                    "math_mode": "tf32 tcgen05 (fp32 accumulate)", "extractor": "default 19-filter bank"},
         "clocks": clocks,

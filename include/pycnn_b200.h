@@ -174,6 +174,15 @@ int pycnn_b200_backward_last(pycnn_b200_ctx* ctx, const int32_t* labels, int bs)
 int pycnn_b200_comm_unique_id(char* id128);
 int pycnn_b200_comm_init(pycnn_b200_ctx* ctx, const char* id128, int rank, int world);
 int pycnn_b200_comm_destroy(pycnn_b200_ctx* ctx);
+/* Peer-memory gradient exchange (pycnn_b200/csrc/p2p.cuh): replaces NCCL all-reduce + norm + update by a fused
+ * reduce-scatter -> norms -> sharded clip/Adam -> all-gather over NVLink peer pointers.  Every rank exports
+ * the CUDA IPC handles of its gradient, parameter and sync buffers (192 bytes, after set_network), the host
+ * layer all-gathers them, and every rank attaches to all `world` blobs (rank order).  world <= 8, one node.
+ * set_network / comm_destroy detach.  Adam m, v are then sharded: a rank only holds state for its range. */
+#define PYCNN_B200_IPC_BLOB_BYTES 192
+int pycnn_b200_comm_ipc_export(pycnn_b200_ctx* ctx, char* blob192);
+int pycnn_b200_comm_ipc_attach(pycnn_b200_ctx* ctx, const char* blobs, int rank, int world);
+int pycnn_b200_comm_ipc_detach(pycnn_b200_ctx* ctx);
 /* device pointer + element count of the flat float32 gradient buffer (for an external
  * all-reduce, e.g. torch.distributed on a wrapped tensor); valid until set_network */
 int pycnn_b200_grad_buffer(pycnn_b200_ctx* ctx, void** device_ptr, int64_t* num_floats);

@@ -79,6 +79,9 @@ _SIGNATURES = {
     "pycnn_b200_comm_unique_id": [ctypes.c_char_p],
     "pycnn_b200_comm_init": [c_ctx, ctypes.c_char_p, I, I],
     "pycnn_b200_comm_destroy": [c_ctx],
+    "pycnn_b200_comm_ipc_export": [c_ctx, ctypes.c_char_p],
+    "pycnn_b200_comm_ipc_attach": [c_ctx, ctypes.c_char_p, I, I],
+    "pycnn_b200_comm_ipc_detach": [c_ctx],
     "pycnn_b200_grad_buffer": [c_ctx, ctypes.POINTER(ctypes.c_void_p), _i64p],
     "pycnn_b200_forward_backward": [c_ctx, _i64p, I],
     "pycnn_b200_apply_update": [c_ctx],
@@ -430,6 +433,18 @@ class Context:
 
     def comm_destroy(self):
         check(self.lib.pycnn_b200_comm_destroy(self.handle))
+
+    def comm_ipc_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(192)
+        check(self.lib.pycnn_b200_comm_ipc_export(self.handle, buf))
+        return buf.raw
+
+    def comm_ipc_attach(self, blobs: bytes, rank: int, world: int):
+        assert len(blobs) == 192 * world
+        check(self.lib.pycnn_b200_comm_ipc_attach(self.handle, blobs, int(rank), int(world)))
+
+    def comm_ipc_detach(self):
+        check(self.lib.pycnn_b200_comm_ipc_detach(self.handle))
 
     def grad_buffer(self):
         p, n = ctypes.c_void_p(), ctypes.c_int64()

@@ -6,6 +6,7 @@
 #include "elementwise.cuh"
 #include "extract_tc.cuh"
 #include "gemm_tc.cuh"
+#include "p2p.cuh"
 #include "simt.cuh"
 
 using namespace pb;
@@ -15,6 +16,7 @@ namespace {
 constexpr int64_t kSlackFloats = 128;  // tail slack behind every fp32 buffer (vector tails, partial tiles)
 
 void drop_graphs(pycnn_b200_ctx* c);
+int p2p_exchange_update(pycnn_b200_ctx* c);
 
 int alloc_f32(float** p, int64_t n) {
   PB_CUDA(cudaMalloc(p, sizeof(float) * (size_t)(n + kSlackFloats)));
@@ -282,6 +284,52 @@ int apply_update(pycnn_b200_ctx* c) {
   return 0;
 }
 
+UpdateParams make_update_params(pycnn_b200_ctx* c) {
+  UpdateParams u{};
+  u.opt = c->opt; u.rule = c->update_rule;
+  u.lr = (float)c->lr; u.beta1 = (float)c->beta1; u.beta2 = (float)c->beta2; u.eps = (float)c->eps;
+  u.eps2 = (float)(c->eps * c->eps); u.max_norm = 5.0f;
+  double bc1 = 1.0, bc2 = 1.0;
+  if (c->opt == PYCNN_B200_OPT_ADAM && c->update_rule == PYCNN_B200_RULE_CPU) {
+    bc1 = 1.0 - c->beta1;
+    bc2 = 1.0 - c->beta2;
+    if (std::fabs(bc1) < 1e-8) bc1 = 1e-8;
+    if (std::fabs(bc2) < 1e-8) bc2 = 1e-8;
+  }
+  u.inv_bc1 = (float)(1.0 / bc1); u.inv_bc2 = (float)(1.0 / bc2);
+  u.beta1_d = c->beta1; u.beta2_d = c->beta2;
+  u.steps_done = c->d_cursor;
+  return u;
+}
+
+// reduce-scatter -> norms -> sharded update -> all-gather over NVLink peer memory (p2p.cuh)
+int p2p_exchange_update(pycnn_b200_ctx* c) {
+  p2p::PeerTable t{};
+  for (int r = 0; r < c->world; ++r) {
+    t.grads[r] = static_cast<float*>(c->p2p_peer_ptrs[0][r]);
+    t.params[r] = static_cast<float*>(c->p2p_peer_ptrs[1][r]);
+    t.sync[r] = static_cast<p2p::SyncBlock*>(c->p2p_peer_ptrs[2][r]);
+  }
+  t.rank = c->rank; t.world = c->world; t.chunk0 = c->p2p_chunk0; t.nchunks = c->p2p_nchunks;
+  const int grid = std::max(1, c->p2p_nchunks);
+  {
+    LaunchScope ls(c, KC_ALLREDUCE);
+    p2p::p2p_reduce_kernel<<<grid, 256, 0, c->stream>>>(t, c->d_chunks, c->d_p2p_seq, c->d_norm_part);
+    PB_CUDA(cudaGetLastError());
+  }
+  if (c->update_rule == PYCNN_B200_RULE_CPU) {
+    LaunchScope ls(c, KC_SQNORM);
+    p2p::p2p_norms_kernel<<<1, 256, 0, c->stream>>>(t, c->d_p2p_seq, c->d_norm_part, c->d_norm2, (int)c->tensors.size());
+    PB_CUDA(cudaGetLastError());
+  }
+  UpdateParams u = make_update_params(c);
+  LaunchScope ls(c, KC_UPDATE);
+  p2p::p2p_update_kernel<<<grid, 256, 0, c->stream>>>(t, c->d_chunks, c->d_p2p_seq, c->d_m, c->d_v, c->d_norm2, u,
+                                                     c->d_blocks_done);
+  PB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // full step on x [bs, Dp] + labels (device).  bs may be 0 on a rank whose slice is empty.
 int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int bs, bool update, int64_t advance = 0) {
   if (bs > 0) {
@@ -298,8 +346,12 @@ int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int 
     PB_CUDA(cudaGetLastError());
   }
   if (update) {
-    PB_TRY(allreduce_grads(c));
-    PB_TRY(apply_update(c));
+    if (c->p2p) {
+      PB_TRY(p2p_exchange_update(c));
+    } else {
+      PB_TRY(allreduce_grads(c));
+      PB_TRY(apply_update(c));
+    }
   }
   return 0;
 }
@@ -416,7 +468,23 @@ int download_f64(pycnn_b200_ctx* c, const float* src, int64_t rows, int64_t cols
   return 0;
 }
 
+void p2p_detach(pycnn_b200_ctx* c) {
+  if (!c->p2p_sync && !c->p2p) return;
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int k = 0; k < 3; ++k)
+    for (int r = 0; r < 8; ++r) {
+      if (c->p2p_peer_ptrs[k][r] && r != c->rank) cudaIpcCloseMemHandle(c->p2p_peer_ptrs[k][r]);
+      c->p2p_peer_ptrs[k][r] = nullptr;
+    }
+  free_dev(c->p2p_sync); c->p2p_sync = nullptr;
+  free_dev(c->d_norm_part); c->d_norm_part = nullptr;
+  free_dev(c->d_p2p_seq); c->d_p2p_seq = nullptr;
+  free_dev(c->d_blocks_done); c->d_blocks_done = nullptr;
+  c->p2p = false;
+}
+
 void free_network(pycnn_b200_ctx* c) {
+  p2p_detach(c);
   free_workspace(c);
   free_dev(c->d_params); free_dev(c->d_grads); free_dev(c->d_m); free_dev(c->d_v);
   free_dev(c->d_chunks); free_dev(c->d_norm2);
@@ -1241,6 +1309,7 @@ int pycnn_b200_comm_init(pycnn_b200_ctx* c, const char* id128, int rank, int wor
 
 int pycnn_b200_comm_destroy(pycnn_b200_ctx* c) {
   PB_CHECK(c, "null context");
+  p2p_detach(c);
   if (c->nccl_comm) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     drop_graphs(c);
@@ -1250,6 +1319,69 @@ int pycnn_b200_comm_destroy(pycnn_b200_ctx* c) {
   }
   c->rank = 0;
   c->world = 1;
+  return 0;
+}
+
+int pycnn_b200_comm_ipc_export(pycnn_b200_ctx* c, char* blob) {
+  CTX_GUARD(c);
+  PB_CHECK(blob, "null argument");
+  PB_CHECK(c->d_params && c->d_grads, "set_network must be called first");
+  PB_CHECK(c->tensors.size() <= (size_t)p2p::MAX_TENSORS, "too many tensors for the peer-memory exchange");
+  PB_CUDA(cudaStreamSynchronize(c->stream));
+  drop_graphs(c);
+  p2p_detach(c);
+  // fresh sync state: zeroed BEFORE the handles travel, so no peer can write into it earlier
+  PB_CUDA(cudaMalloc(&c->p2p_sync, sizeof(p2p::SyncBlock)));
+  PB_CUDA(cudaMemset(c->p2p_sync, 0, sizeof(p2p::SyncBlock)));
+  PB_CUDA(cudaMalloc(&c->d_norm_part, sizeof(double) * p2p::MAX_TENSORS));
+  PB_CUDA(cudaMemset(c->d_norm_part, 0, sizeof(double) * p2p::MAX_TENSORS));
+  PB_CUDA(cudaMalloc(&c->d_p2p_seq, 2 * sizeof(long long)));
+  PB_CUDA(cudaMalloc(&c->d_blocks_done, sizeof(unsigned int)));
+  PB_CUDA(cudaMemset(c->d_blocks_done, 0, sizeof(unsigned int)));
+  const long long init[2] = {0, 0};
+  PB_CUDA(cudaMemcpy(c->d_p2p_seq, init, sizeof(init), cudaMemcpyHostToDevice));
+  cudaIpcMemHandle_t h[3];
+  PB_CUDA(cudaIpcGetMemHandle(&h[0], c->d_grads));
+  PB_CUDA(cudaIpcGetMemHandle(&h[1], c->d_params));
+  PB_CUDA(cudaIpcGetMemHandle(&h[2], c->p2p_sync));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(blob, h, sizeof(h));
+  return 0;
+}
+
+int pycnn_b200_comm_ipc_attach(pycnn_b200_ctx* c, const char* blobs, int rank, int world) {
+  CTX_GUARD(c);
+  PB_CHECK(blobs && world >= 1 && world <= p2p::MAX_RANKS && rank >= 0 && rank < world, "bad arguments");
+  PB_CHECK(c->p2p_sync, "comm_ipc_export must be called first");
+  PB_CHECK(c->world == world && c->rank == rank, "comm_init(rank, world) must match the peer-memory attach");
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      c->p2p_peer_ptrs[0][r] = c->d_grads; c->p2p_peer_ptrs[1][r] = c->d_params; c->p2p_peer_ptrs[2][r] = c->p2p_sync;
+      continue;
+    }
+    cudaIpcMemHandle_t h[3];
+    memcpy(h, blobs + (size_t)r * PYCNN_B200_IPC_BLOB_BYTES, sizeof(h));
+    for (int k = 0; k < 3; ++k) {
+      void* ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, h[k], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        p2p_detach(c);
+        return fail("cudaIpcOpenMemHandle(rank %d, buffer %d) failed: %s", r, k, cudaGetErrorString(e));
+      }
+      c->p2p_peer_ptrs[k][r] = ptr;
+    }
+  }
+  const int nc = c->num_chunks;
+  c->p2p_chunk0 = (int)((int64_t)rank * nc / world);
+  c->p2p_nchunks = (int)((int64_t)(rank + 1) * nc / world) - c->p2p_chunk0;
+  c->p2p = true;
+  return 0;
+}
+
+int pycnn_b200_comm_ipc_detach(pycnn_b200_ctx* c) {
+  CTX_GUARD(c);
+  drop_graphs(c);
+  p2p_detach(c);
   return 0;
 }
 

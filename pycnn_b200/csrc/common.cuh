@@ -183,6 +183,14 @@ struct pycnn_b200_ctx {
   // comm
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  // peer-memory exchange (p2p.cuh): opened IPC mappings of every rank's buffers
+  bool p2p = false;
+  void* p2p_sync = nullptr;                 // my SyncBlock (peers write into it)
+  void* p2p_peer_ptrs[3][8] = {};           // [grads|params|sync][rank], own entries point at local buffers
+  double* d_norm_part = nullptr;            // per-tensor partial ||g||^2 of my chunk range
+  long long* d_p2p_seq = nullptr;           // [0] unused, [1] exchange sequence number (monotonic since attach)
+  unsigned int* d_blocks_done = nullptr;
+  int p2p_chunk0 = 0, p2p_nchunks = 0;
 
   // timing
   bool timing = false;

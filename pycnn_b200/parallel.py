@@ -60,7 +60,7 @@ def broadcast_bytes(payload: bytes | None, src: int = 0) -> bytes:
     return box[0]
 
 
-def attach(model, make_unique_id=None):
+def attach(model, make_unique_id=None, peer_memory=True):
     """Join `model` (a cuda(True) PyCNN) to the job's NCCL communicator.  No-op for world == 1."""
     from . import _lib
     rank, world, _ = dist_env()
@@ -73,7 +73,21 @@ def attach(model, make_unique_id=None):
     uid = (make_unique_id or _lib.comm_unique_id)() if rank == 0 else None
     uid = broadcast_bytes(uid, src=0)
     model._require().comm_init(uid, rank, world)
+    if peer_memory and world <= 8 and getattr(model, "weights", None):
+        model._bind_network()
+        attach_peer_memory(model._require(), rank, world)
     return rank, world
+
+
+def attach_peer_memory(ctx, rank, world):
+    """After comm_init and set_network on every rank: exchange the CUDA IPC handles of the gradient / parameter /
+    sync buffers and switch the step to the fused peer-memory exchange (csrc/p2p.cuh).  Collective."""
+    import torch.distributed as dist
+    blob = ctx.comm_ipc_export()                 # also zeroes this rank's sync block before anyone can see it
+    blobs = [None] * world
+    dist.all_gather_object(blobs, blob)
+    ctx.comm_ipc_attach(b"".join(blobs), rank, world)
+    dist.barrier()                               # nobody steps before everybody is attached
 
 
 def allreduce_scalars(values, op="sum"):
