@@ -314,18 +314,13 @@ int p2p_exchange_update(pycnn_b200_ctx* c) {
   const int grid = std::max(1, c->p2p_nchunks);
   {
     LaunchScope ls(c, KC_ALLREDUCE);
-    p2p::p2p_reduce_kernel<<<grid, 256, 0, c->stream>>>(t, c->d_chunks, c->d_p2p_seq, c->d_norm_part);
-    PB_CUDA(cudaGetLastError());
-  }
-  if (c->update_rule == PYCNN_B200_RULE_CPU) {
-    LaunchScope ls(c, KC_SQNORM);
-    p2p::p2p_norms_kernel<<<1, 256, 0, c->stream>>>(t, c->d_p2p_seq, c->d_norm_part, c->d_norm2, (int)c->tensors.size());
+    p2p::p2p_reduce_kernel<<<grid, 256, 0, c->stream>>>(t, c->d_chunks, c->d_p2p_seq, c->d_norm_part,
+                                                        (int)c->tensors.size(), c->d_blocks_done);
     PB_CUDA(cudaGetLastError());
   }
   UpdateParams u = make_update_params(c);
   LaunchScope ls(c, KC_UPDATE);
-  p2p::p2p_update_kernel<<<grid, 256, 0, c->stream>>>(t, c->d_chunks, c->d_p2p_seq, c->d_m, c->d_v, c->d_norm2, u,
-                                                     c->d_blocks_done);
+  p2p::p2p_update_kernel<<<grid, 256, 0, c->stream>>>(t, c->d_chunks, c->d_p2p_seq, c->d_m, c->d_v, u, c->d_blocks_done + 1);
   PB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1336,8 +1331,8 @@ int pycnn_b200_comm_ipc_export(pycnn_b200_ctx* c, char* blob) {
   PB_CUDA(cudaMalloc(&c->d_norm_part, sizeof(double) * p2p::MAX_TENSORS));
   PB_CUDA(cudaMemset(c->d_norm_part, 0, sizeof(double) * p2p::MAX_TENSORS));
   PB_CUDA(cudaMalloc(&c->d_p2p_seq, 2 * sizeof(long long)));
-  PB_CUDA(cudaMalloc(&c->d_blocks_done, sizeof(unsigned int)));
-  PB_CUDA(cudaMemset(c->d_blocks_done, 0, sizeof(unsigned int)));
+  PB_CUDA(cudaMalloc(&c->d_blocks_done, 2 * sizeof(unsigned int)));
+  PB_CUDA(cudaMemset(c->d_blocks_done, 0, 2 * sizeof(unsigned int)));
   const long long init[2] = {0, 0};
   PB_CUDA(cudaMemcpy(c->d_p2p_seq, init, sizeof(init), cudaMemcpyHostToDevice));
   cudaIpcMemHandle_t h[3];

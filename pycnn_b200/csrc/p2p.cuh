@@ -9,16 +9,16 @@
 //                          ready" flags from all ranks, sums its range over all ranks' gradient buffers with
 //                          128-bit loads across NVLink (fixed rank order: deterministic), stores the reduced
 //                          gradient locally and accumulates per-tensor ||g||^2 partials;        (reduce-scatter)
-//   B  p2p_norms_kernel    one block: publishes the partials to every peer, waits for theirs, sums them in rank
-//                          order -> the norms of the fully reduced gradient, identical on every rank;
-//   C  p2p_update_kernel   clip / skip / SGD / Adam on the owned range only (optimizer state is sharded: m and v
+//                          its last block publishes the partials to every peer;
+//   C  p2p_update_kernel   waits for all ranks' partials and sums them in rank order (the norms of the fully
+//                          reduced gradient, identical on every rank); clip / skip / SGD / Adam on the owned range only (optimizer state is sharded: m and v
 //                          of a chunk are only ever touched by its owner) and 128-bit stores of the new
 //                          parameters into EVERY rank's parameter buffer; the last block publishes "params
 //                          written" and waits for all peers' flags, so the kernel retires only when this
 //                          rank's parameters are complete.                                        (all-gather)
 //
 // Flags are monotonically increasing step sequence numbers written with st.release.sys / read with
-// ld.acquire.sys; all spins are bounded (trap, never hang).  Every rank runs the same three launches every
+// ld.acquire.sys; all spins are bounded (trap, never hang).  Every rank runs the same two launches every
 // step (also with an empty shard), each on its own GPU.
 #pragma once
 #include "elementwise.cuh"
@@ -57,8 +57,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long seq) {
   unsigned int polls = 0;
   while (ld_acquire_sys(p) < seq) {
-    __nanosleep(64);
-    if (++polls > (1u << 26)) __trap();
+    if (++polls > 64u) __nanosleep(32);
+    if (polls > (1u << 26)) __trap();
   }
 }
 // Gradients of other ranks change every step at the same addresses: never read them through the non-coherent
@@ -77,7 +77,8 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {
 // while attached, advanced by the last block of p2p_update_kernel), so flags only ever increase.
 __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chunk* __restrict__ chunks,
                                                          const long long* __restrict__ seq_ptr,
-                                                         double* __restrict__ norm_part) {
+                                                         double* __restrict__ norm_part, int ntensors,
+                                                         unsigned int* __restrict__ blocks_done) {
   const unsigned long long seq = (unsigned long long)seq_ptr[1] + 1ull;   // exchanges completed since attach + 1
   if (blockIdx.x == 0 && threadIdx.x < t.world) {
     __threadfence_system();   // my backward pass (previous kernels of this stream) is visible system-wide
@@ -85,71 +86,77 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chun
   }
   if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->grads_ready[threadIdx.x], seq);
   __syncthreads();
-  if ((int)blockIdx.x >= t.nchunks) return;
-  const Chunk ch = chunks[t.chunk0 + blockIdx.x];
-  const int64_t n4 = ch.len >> 2;
-  float4* mine = reinterpret_cast<float4*>(t.grads[t.rank] + ch.off);
-  float acc = 0.f;
-  for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < t.world; ++r) {          // fixed order: the sum is bit-identical run to run
-      const float4 v = ld_peer(reinterpret_cast<const float4*>(t.grads[r] + ch.off) + i);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
-    mine[i] = s;
-    acc = fmaf(s.x, s.x, acc); acc = fmaf(s.y, s.y, acc); acc = fmaf(s.z, s.z, acc); acc = fmaf(s.w, s.w, acc);
-  }
-  double d = warp_sum_d((double)acc);
   __shared__ double sh[8];
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = d;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double tot = 0.0;
-    for (int i = 0; i < 8; ++i) tot += sh[i];
-    atomicAdd(&norm_part[ch.tensor], tot);
+  if ((int)blockIdx.x < t.nchunks) {
+    const Chunk ch = chunks[t.chunk0 + blockIdx.x];
+    const int64_t n4 = ch.len >> 2;
+    float4* mine = reinterpret_cast<float4*>(t.grads[t.rank] + ch.off);
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < t.world; ++r) {          // fixed order: the sum is bit-identical run to run
+        const float4 v = ld_peer(reinterpret_cast<const float4*>(t.grads[r] + ch.off) + i);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      mine[i] = s;
+      acc = fmaf(s.x, s.x, acc); acc = fmaf(s.y, s.y, acc); acc = fmaf(s.z, s.z, acc); acc = fmaf(s.w, s.w, acc);
+    }
+    const double d = warp_sum_d((double)acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int i = 0; i < 8; ++i) tot += sh[i];
+      atomicAdd(&norm_part[ch.tensor], tot);
+    }
   }
-}
-
-// ---- B: exchange partial norms --------------------------------------------------------------------------
-// one block of 256 threads; ntensors <= MAX_TENSORS
-__global__ void __launch_bounds__(256) p2p_norms_kernel(PeerTable t, const long long* __restrict__ seq_ptr,
-                                                        double* __restrict__ norm_part, double* __restrict__ norm2,
-                                                        int ntensors) {
-  const unsigned long long seq = (unsigned long long)seq_ptr[1] + 1ull;   // exchanges completed since attach + 1
-  for (int i = threadIdx.x; i < t.world * ntensors; i += blockDim.x) {
-    const int r = i / ntensors, k = i - r * ntensors;
-    t.sync[r]->norms[t.rank][k] = norm_part[k];
-  }
-  __threadfence_system();
+  // the last block to finish publishes this rank's per-tensor partial norms to every rank
+  __threadfence();
   __syncthreads();
-  if (threadIdx.x < t.world) st_release_sys(&t.sync[threadIdx.x]->norms_ready[t.rank], seq);
-  if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->norms_ready[threadIdx.x], seq);
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(blocks_done, 1u) == gridDim.x - 1);
   __syncthreads();
-  for (int k = threadIdx.x; k < ntensors; k += blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < t.world; ++r) s += __ldcv(&t.sync[t.rank]->norms[r][k]);   // rank order: identical everywhere
-    norm2[k] = s;
-    norm_part[k] = 0.0;                                                   // ready for the next step
+  if (last) {
+    for (int i = threadIdx.x; i < t.world * ntensors; i += blockDim.x) {
+      const int r = i / ntensors, k = i - r * ntensors;
+      t.sync[r]->norms[t.rank][k] = __ldcg(&norm_part[k]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < t.world) st_release_sys(&t.sync[threadIdx.x]->norms_ready[t.rank], seq);
+    for (int k = threadIdx.x; k < ntensors; k += blockDim.x) norm_part[k] = 0.0;   // ready for the next step
+    if (threadIdx.x == 0) *blocks_done = 0u;
   }
 }
 
 // ---- C: sharded clip + update, all-gather of the new parameters ------------------------------------------
 __global__ void __launch_bounds__(256) p2p_update_kernel(PeerTable t, const Chunk* __restrict__ chunks,
                                                          long long* __restrict__ seq_ptr, float* __restrict__ m,
-                                                         float* __restrict__ v, const double* __restrict__ norm2,
-                                                         UpdateParams u, unsigned int* __restrict__ blocks_done) {
+                                                         float* __restrict__ v, UpdateParams u,
+                                                         unsigned int* __restrict__ blocks_done) {
   const unsigned long long seq = (unsigned long long)seq_ptr[1] + 1ull;   // exchanges completed since attach + 1
+  __shared__ double s_n2;
   if ((int)blockIdx.x < t.nchunks) {
     const Chunk ch = chunks[t.chunk0 + blockIdx.x];
     float scale = 1.0f;
     bool skip = false;
+    if (u.rule == 0) {   // norms of the fully reduced gradient: every rank's partials, summed in rank order
+      if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->norms_ready[threadIdx.x], seq);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double n2 = 0.0;
+        for (int r = 0; r < t.world; ++r) n2 += __ldcv(&t.sync[t.rank]->norms[r][ch.tensor]);
+        s_n2 = n2;
+      }
+      __syncthreads();
+    }
     if (u.rule == 1 && u.opt == 1) {
       const double tt = (double)max((long long)u.steps_done[1], 1ll);   // Adam step count kept by the softmax kernel
       u.inv_bc1 = (float)(1.0 / (1.0 - pow(u.beta1_d, tt)));
       u.inv_bc2 = (float)(1.0 / (1.0 - pow(u.beta2_d, tt)));
     }
     if (u.rule == 0) {
-      const double n2 = norm2[ch.tensor];
+      const double n2 = s_n2;
       if (!isfinite(n2)) skip = true;            // NaN/Inf gradient: this tensor keeps its value on every rank
       const double nrm = sqrt(n2);
       if (!skip && nrm > (double)u.max_norm) scale = (float)((double)u.max_norm / nrm);
