@@ -178,7 +178,7 @@ int forward_logits(pycnn_b200_ctx* c, const float* x, int bs) {
     g.B = c->d_params + Wt(c, l).off; g.ldb = Wt(c, l).ld; g.b_kmajor = true;
     g.M = bs; g.N = (int)c->dims[l + 1]; g.K = (int)c->dims[l];
     g.bias = c->d_params + Bt(c, l).off;
-    g.cls = KC_GEMM_FWD;
+    g.cls = (l == 0) ? KC_GEMM_FWD1 : KC_GEMM_FWD;
     if (l < c->L) { g.C = c->d_act[l]; g.epi = 2; }
     else          { g.C = c->d_probs;  g.epi = 1; }
     g.ldc = c->ldw[l + 1];
@@ -202,12 +202,10 @@ int softmax_ce(pycnn_b200_ctx* c, int bs, const int32_t* labels, bool write_prob
     db = c->d_grads + c->tensors[2 * c->L + 1].off;
     smem = sizeof(float) * (size_t)c->C;
   }
-  softmax_ce_kernel<<<blocks, 256, smem, c->stream>>>(c->d_probs, bs, c->C, c->ldw[c->L + 1], labels,
-                                                      write_probs ? c->d_probs : nullptr,
-                                                      write_dz ? c->d_dz[c->L] : nullptr,
-                                                      write_pred ? c->d_pred : nullptr, write_pred ? c->d_conf : nullptr,
-                                                      stats ? c->d_stats : nullptr, db, bk);
-  PB_CUDA(cudaGetLastError());
+  PB_CUDA(launch_pdl(c, softmax_ce_kernel, dim3(blocks), dim3(256), smem, c->stream, (const float*)c->d_probs, bs, c->C,
+                     c->ldw[c->L + 1], labels, write_probs ? c->d_probs : (float*)nullptr,
+                     write_dz ? c->d_dz[c->L] : (float*)nullptr, write_pred ? c->d_pred : (int32_t*)nullptr,
+                     write_pred ? c->d_conf : (float*)nullptr, stats ? c->d_stats : (double*)nullptr, db, bk));
   return 0;
 }
 
@@ -228,7 +226,7 @@ int backward(pycnn_b200_ctx* c, const float* x, int bs) {
       g.A = c->d_dz[l]; g.lda = c->ldw[l + 1]; g.a_kmajor = false;
       g.B = in; g.ldb = c->ldw[l]; g.b_kmajor = false;
       g.C = c->d_grads + Wt(c, l).off; g.ldc = Wt(c, l).ld;
-      g.M = out_n; g.N = in_n; g.K = bs; g.epi = 0; g.cls = KC_GEMM_DW;
+      g.M = out_n; g.N = in_n; g.K = bs; g.epi = 0; g.cls = (l == 0) ? KC_GEMM_DW1 : KC_GEMM_DW;
       g.c_is_zero = true;
       PB_TRY(gemm(c, g));
     }
@@ -274,13 +272,12 @@ int apply_update(pycnn_b200_ctx* c) {
   u.steps_done = c->d_cursor;   // CuPy rule: bias corrections from the device-side step count (graph-replayable)
   if (c->update_rule == PYCNN_B200_RULE_CPU) {   // d_norm2 was zeroed by this step's softmax kernel
     LaunchScope ls(c, KC_SQNORM);
-    grad_sqnorm_kernel<<<c->num_chunks, 256, 0, c->stream>>>(c->d_grads, c->d_chunks, c->d_norm2);
-    PB_CUDA(cudaGetLastError());
+    PB_CUDA(launch_pdl(c, grad_sqnorm_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, (const float*)c->d_grads,
+                       (const Chunk*)c->d_chunks, c->d_norm2));
   }
   LaunchScope ls(c, KC_UPDATE);
-  clip_update_kernel<<<c->num_chunks, 256, 0, c->stream>>>(c->d_params, c->d_grads, c->d_m, c->d_v, c->d_chunks,
-                                                           c->d_norm2, u);
-  PB_CUDA(cudaGetLastError());
+  PB_CUDA(launch_pdl(c, clip_update_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, c->d_params,
+                     (const float*)c->d_grads, c->d_m, c->d_v, (const Chunk*)c->d_chunks, (const double*)c->d_norm2, u));
   return 0;
 }
 
@@ -314,14 +311,13 @@ int p2p_exchange_update(pycnn_b200_ctx* c) {
   const int grid = std::max(1, c->p2p_nchunks);
   {
     LaunchScope ls(c, KC_ALLREDUCE);
-    p2p::p2p_reduce_kernel<<<grid, 256, 0, c->stream>>>(t, c->d_chunks, c->d_p2p_seq, c->d_norm_part,
-                                                        (int)c->tensors.size(), c->d_blocks_done);
-    PB_CUDA(cudaGetLastError());
+    PB_CUDA(launch_pdl(c, p2p::p2p_reduce_kernel, dim3(grid), dim3(256), 0, c->stream, t, (const Chunk*)c->d_chunks,
+                       (const long long*)c->d_p2p_seq, c->d_norm_part, (int)c->tensors.size(), c->d_blocks_done));
   }
   UpdateParams u = make_update_params(c);
   LaunchScope ls(c, KC_UPDATE);
-  p2p::p2p_update_kernel<<<grid, 256, 0, c->stream>>>(t, c->d_chunks, c->d_p2p_seq, c->d_m, c->d_v, u, c->d_blocks_done + 1);
-  PB_CUDA(cudaGetLastError());
+  PB_CUDA(launch_pdl(c, p2p::p2p_update_kernel, dim3(grid), dim3(256), 0, c->stream, t, (const Chunk*)c->d_chunks,
+                     c->d_p2p_seq, c->d_m, c->d_v, u, c->d_blocks_done + 1));
   return 0;
 }
 
@@ -356,9 +352,8 @@ int gather_batch(pycnn_b200_ctx* c, const int64_t* d_idx, const int64_t* cursor,
   if (bs == 0) return 0;
   LaunchScope ls(c, KC_GATHER);
   const int64_t total = (int64_t)bs * (c->Dp >> 2);
-  gather_rows_kernel<<<grid_for(total, 256, c->num_sms), 256, 0, c->stream>>>(c->d_feat, c->d_labels, d_idx, cursor, extra, bs,
-                                                                              c->Dp, c->d_x, c->d_blabels);
-  PB_CUDA(cudaGetLastError());
+  PB_CUDA(launch_pdl(c, gather_rows_kernel, dim3(grid_for(total, 256, c->num_sms)), dim3(256), 0, c->stream, c->d_feat,
+                     c->d_labels, d_idx, cursor, extra, bs, c->Dp, c->d_x, c->d_blabels));
   return 0;
 }
 
@@ -546,6 +541,7 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   CREATE_CUDA(cudaMemset(c->d_cursor, 0, 2 * sizeof(int64_t)));
 #undef CREATE_CUDA
   { const char* g = getenv("PYCNN_B200_GRAPHS"); if (g && g[0] == '0') c->use_graphs = false; }
+  { const char* g = getenv("PYCNN_B200_PDL"); if (g && g[0] == '0') c->use_pdl = false; }
   if (tc_gemm_prepare(c) != 0 || tc_extract_prepare(c) != 0) return bail(1);
   if (resolve_encode_tiled(c) != 0) return bail(1);
   *out = c;

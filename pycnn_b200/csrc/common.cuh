@@ -58,9 +58,11 @@ static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
 enum KernelClass : int {
   KC_EXTRACT = 0,   // fused conv3x3 + ReLU + 2x2 max-pool + flatten
   KC_GATHER,        // batch row gather
-  KC_GEMM_FWD,      // forward GEMMs (bias/ReLU epilogue)
-  KC_GEMM_DA,       // backward dA GEMMs (ReLU-mask epilogue)
-  KC_GEMM_DW,       // backward dW GEMMs
+  KC_GEMM_FWD,      // forward GEMMs of layers 2..L+1 (bias/ReLU epilogue)
+  KC_GEMM_DA,       // backward dA GEMMs (ReLU-mask epilogue, fused bias gradient)
+  KC_GEMM_DW,       // backward dW GEMMs of layers 2..L+1
+  KC_GEMM_FWD1,     // forward GEMM of layer 1: [bs, D] x [D, n1] -- the dominant forward kernel
+  KC_GEMM_DW1,      // dW of layer 1: [n1, bs] x [bs, D] -- the dominant backward kernel
   KC_SOFTMAX_CE,    // softmax + CE + argmax + dZ
   KC_COLSUM,        // bias gradients
   KC_SQNORM,        // per-tensor gradient norms
@@ -71,7 +73,8 @@ enum KernelClass : int {
 };
 
 static const char* const kKernelClassNames[KC_COUNT] = {
-    "extract_conv_relu_pool", "gather_rows", "gemm_forward", "gemm_dA", "gemm_dW", "softmax_ce_grad",
+    "extract_conv_relu_pool", "gather_rows", "gemm_forward_tail", "gemm_dA", "gemm_dW_tail", "gemm_forward_layer1",
+    "gemm_dW_layer1", "softmax_ce_grad",
     "bias_colsum", "grad_sqnorm", "clip_update", "allreduce", "misc"};
 
 struct TimedLaunch {
@@ -211,6 +214,7 @@ struct pycnn_b200_ctx {
   };
   std::map<std::tuple<int, int64_t, int64_t, int64_t, int>, GraphEntry> graphs;
   bool use_graphs = true;
+  bool use_pdl = true;           // programmatic dependent launch between the step's kernels (PYCNN_B200_PDL=0 disables)
   int64_t* d_cursor = nullptr;   // [0] offset into d_idx of the current batch, [1] completed steps (device-side t)
 };
 
@@ -247,6 +251,27 @@ struct LaunchScope {
     return e;
   }
 };
+
+// Programmatic dependent launch: the next kernel of the step may start launching (and run its prologue) while
+// this one drains; every kernel calls pdl_wait() before it touches global memory produced by its predecessor.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(pycnn_b200_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = c->use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 static inline int ensure_scratch(pycnn_b200_ctx* c, size_t bytes) {
   if (bytes <= c->scratch_cap) return 0;

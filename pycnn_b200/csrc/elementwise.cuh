@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
                                                           const int64_t* __restrict__ cursor, int64_t extra, int bs,
                                                           int64_t Dp, float* __restrict__ x,
                                                           int32_t* __restrict__ blabels) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t* __restrict__ idx = idx_base + (cursor ? cursor[0] : 0) + extra;
   const int64_t vec_per_row = Dp >> 2;
   const int64_t total = (int64_t)bs * vec_per_row;
@@ -103,6 +105,7 @@ struct StepBookkeeping {   // per-step housekeeping folded into the softmax kern
 };
 
 __global__ void step_bookkeeping_kernel(StepBookkeeping bk) {   // ranks whose shard of a batch is empty
+  pdl_wait();
   if (bk.norm2 && (int)threadIdx.x < bk.n_norm) bk.norm2[threadIdx.x] = 0.0;
   if (bk.cursor && threadIdx.x == 0) { bk.cursor[0] += bk.advance; bk.cursor[1] += 1; }
 }
@@ -114,6 +117,8 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
                                                          double* __restrict__ stats, float* __restrict__ db,
                                                          StepBookkeeping bk) {
   extern __shared__ float s_db[];   // [C] when db != nullptr: block-level bias-gradient partial sums
+  pdl_wait();
+  pdl_launch_dependents();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -193,6 +198,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dz, int bs, int N, int64_t ld,
                                                      float* __restrict__ db, int rows_per_block, int accumulate) {
   __shared__ double red[8][33];
+  pdl_wait();
   const int n = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(bs, r0 + rows_per_block);
@@ -217,6 +223,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restrict__ grads,
                                                           const Chunk* __restrict__ chunks,
                                                           double* __restrict__ norm2) {
+  pdl_wait();
+  pdl_launch_dependents();
   const Chunk ch = chunks[blockIdx.x];
   const float4* g4 = reinterpret_cast<const float4*>(grads + ch.off);
   const int64_t n4 = ch.len >> 2;  // chunk offsets/lengths are multiples of 4
@@ -257,6 +265,8 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ pa
                                                           float* __restrict__ m, float* __restrict__ v,
                                                           const Chunk* __restrict__ chunks,
                                                           const double* __restrict__ norm2, UpdateParams u) {
+  pdl_wait();
+  pdl_launch_dependents();
   const Chunk ch = chunks[blockIdx.x];
   float scale = 1.0f;
   if (u.rule == 1 && u.opt == 1) {   // pycnn/pycnn.py:534,544-545: t advances, 1 - beta^t
@@ -344,6 +354,8 @@ __global__ void f32_padded_to_f32_kernel(const float* __restrict__ src, int64_t 
 __global__ void gemm_fixup_kernel(float* __restrict__ c, int M, int N, int64_t ldc, int epi,
                                   const float* __restrict__ bias, const float* __restrict__ mask,
                                   int64_t ldmask) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t total = (int64_t)M * N;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {

@@ -153,6 +153,8 @@ __global__ void __launch_bounds__(128 * MAX_WG, 1) extract_tc_kernel(const __gri
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
+  pdl_wait();                 // the images (H2D copy or a previous kernel) are complete from here on
+  pdl_launch_dependents();
   const uint32_t tmem_acc = *tmem_slot + (uint32_t)(wg * a.wg_cols);
   const uint32_t lane_taddr = tmem_acc + (static_cast<uint32_t>((warp & 3) * 32) << 16);
 
@@ -396,8 +398,7 @@ static inline int tc_extract(pycnn_b200_ctx* c, const uint8_t* d_images, int64_t
     PB_CHECK((reinterpret_cast<uintptr_t>(a.images) & 15) == 0, "image batch is not 16-byte aligned");
     const int grid = (int)std::min<int64_t>(ceil_div(a.num_tiles, nwg), c->num_sms);
     LaunchScope ls(c, KC_EXTRACT);
-    tcx::extract_tc_kernel<<<grid, 128 * nwg, smem_bytes, c->stream>>>(a);
-    PB_CUDA(cudaGetLastError());
+    PB_CUDA(launch_pdl(c, tcx::extract_tc_kernel, dim3(grid), dim3(128 * nwg), smem_bytes, c->stream, a));
   }
   return 0;
 }

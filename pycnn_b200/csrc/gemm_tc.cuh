@@ -93,6 +93,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -362,8 +365,7 @@ static int launch_tc_gemm(pycnn_b200_ctx* c, const GemmCall& g, const CUtensorMa
                           const tc::TcGemmArgs& args, dim3 grid) {
   using Cfg = tc::GemmCfg<BN>;
   auto kern = tc::gemm_tf32_kernel<BN, A_MN, B_MN>;
-  kern<<<grid, 192, Cfg::SMEM_BYTES, c->stream>>>(ma, mb, args);
-  PB_CUDA(cudaGetLastError());
+  PB_CUDA(launch_pdl(c, kern, grid, dim3(192), (size_t)Cfg::SMEM_BYTES, c->stream, ma, mb, args));
   return 0;
 }
 
@@ -412,7 +414,7 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   a.colsum = g.colsum;
   dim3 grid(tiles_n, tiles_m, split);
   if (split > 1 && !g.c_is_zero) {
-    LaunchScope ls(c, KC_MISC);
+    LaunchScope ls(c, g.cls);   // the split-K zero-fill and fix-up are part of this GEMM's cost
     PB_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * ((size_t)(g.M - 1) * g.ldc + g.N), c->stream));
   }
   {
@@ -422,11 +424,11 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
     else PB_TRY((dispatch_bn<true, true>(c, BN, g, ma, mb, a, grid)));
   }
   if (split > 1 && g.epi != 0) {
-    LaunchScope ls(c, KC_MISC);
+    LaunchScope ls(c, g.cls);
     const int64_t total = (int64_t)g.M * g.N;
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 8 * c->num_sms);
-    gemm_fixup_kernel<<<blocks, 256, 0, c->stream>>>(g.C, g.M, g.N, g.ldc, g.epi, g.bias, g.mask, g.ldmask);
-    PB_CUDA(cudaGetLastError());
+    PB_CUDA(launch_pdl(c, gemm_fixup_kernel, dim3(blocks), dim3(256), 0, c->stream, g.C, g.M, g.N, g.ldc, g.epi, g.bias,
+                       g.mask, g.ldmask));
   }
   return 0;
 }

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chun
                                                          const long long* __restrict__ seq_ptr,
                                                          double* __restrict__ norm_part, int ntensors,
                                                          unsigned int* __restrict__ blocks_done) {
+  pdl_wait();
   const unsigned long long seq = (unsigned long long)seq_ptr[1] + 1ull;   // exchanges completed since attach + 1
   if (blockIdx.x == 0 && threadIdx.x < t.world) {
     __threadfence_system();   // my backward pass (previous kernels of this stream) is visible system-wide
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(256) p2p_update_kernel(PeerTable t, const Chun
                                                          long long* __restrict__ seq_ptr, float* __restrict__ m,
                                                          float* __restrict__ v, UpdateParams u,
                                                          unsigned int* __restrict__ blocks_done) {
+  pdl_wait();
   const unsigned long long seq = (unsigned long long)seq_ptr[1] + 1ull;   // exchanges completed since attach + 1
   __shared__ double s_n2;
   if ((int)blockIdx.x < t.nchunks) {

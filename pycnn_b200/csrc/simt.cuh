@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256) extract_simt_kernel(const uint8_t* __rest
                                                            int PW, int F, const float* __restrict__ taps,
                                                            float* __restrict__ out, int64_t ld, int tiles_x) {
   extern __shared__ float smem[];
+  pdl_wait();
   float* s_sum = smem;                       // [EX_IN][EX_IN+1]
   float* s_taps = smem + EX_IN * (EX_IN + 1);  // [F][9]
   const int n = blockIdx.y;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(256) sgemm_simt_kernel(SimtGemmArgs g) {
   constexpr int BM = 64, BN = 64, BK = 16;
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
+  pdl_wait();
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
