@@ -375,6 +375,65 @@ def test_config2_full_size_step_properties(lib, ctx, mode, tol):
     np.testing.assert_array_equal(p1.argmax(1)[clear], want_p.argmax(1)[clear])
 
 
+@pytest.mark.parametrize("name,S,F,C,layers,bs", [
+    ("config3", 64, 19, 100, [1024, 512, 256], 192),      # BASELINE configs[2]: D = 18259
+    ("config5", 224, 8, 1000, [2048, 1024, 512], 48),     # BASELINE configs[4] with the custom 8-filter bank: D = 98568
+])
+@pytest.mark.parametrize("mode,tol", [("fp32", FP32_TOL), ("tf32", TF32_TOL)])
+def test_large_config_shapes_step_parity(lib, ctx, mode, tol, name, S, F, C, layers, bs):
+    """The other BASELINE configurations at their real layer widths (reduced batch so the oracle finishes in
+    seconds): extractor -> forward -> CE -> backward against the oracle, then one clipped Adam step."""
+    filt = O.DEFAULT_FILTERS if F == 19 else custom_filters(F)
+    ctx.set_math_mode(lib.MATH_FP32_SIMT if mode == "fp32" else lib.MATH_TF32)
+    ctx.set_extract_mode(lib.EXTRACT_SIMT if mode == "fp32" else lib.EXTRACT_TC)
+    ctx.set_filters(filt)
+    D = ctx.feature_count(S)
+    assert D == O.feature_count(S, F)
+    ctx.set_network(D, layers, C)
+    rng = np.random.default_rng(5)
+    dims = [D] + layers + [C]
+    w, b = {}, {}
+    wk, bk = O.layer_keys(len(layers))
+    for l, (wn, bn) in enumerate(zip(wk, bk)):        # He-normal like _init_layers, drawn in float32 to keep it quick
+        w[wn] = (rng.standard_normal((dims[l + 1], dims[l]), dtype=np.float32) * np.float32((2 / dims[l]) ** 0.5)).astype(np.float64)
+        b[bn] = rng.standard_normal(dims[l + 1]) * 0.01
+        ctx.set_param(2 * l, w[wn])
+        ctx.set_param(2 * l + 1, b[bn])
+    ctx.set_optimizer(lib.OPT_ADAM, 1e-4)
+    imgs, lab = synth_images(bs, S, 31), synth_labels(bs, C, 32)
+    ctx.dataset_alloc(bs)
+    ctx.dataset_extract(0, imgs)
+    ctx.dataset_set_labels(0, lab)
+    feats = ctx.dataset_get_features(0, bs)
+    assert rel_err(feats, O.extract_batch(imgs, filt)) < FP32_TOL
+    idx = np.arange(bs)
+    p_dev = ctx.forward_rows(row0=0, bs=bs)
+    p, acts, _ = O.forward(feats, w, b, layers)
+    assert rel_err(p_dev, p) < tol, rel_err(p_dev, p)
+    gap = np.sort(p, axis=1)
+    clear = (gap[:, -1] - gap[:, -2]) > (0 if mode == "fp32" else 0.02 * gap[:, -1])
+    np.testing.assert_array_equal(p_dev.argmax(1)[clear], p.argmax(1)[clear])
+    ctx.forward_backward(idx)
+    gw, gb = O.backward(p, O.one_hot(lab, C), acts, w, layers)
+    errs = {}
+    for l, (wn, bn) in enumerate(zip(wk, bk)):
+        errs[wn] = rel_err(ctx.get_grad(2 * l), gw[wn])
+        errs[bn] = rel_err(ctx.get_grad(2 * l + 1), gb[bn])
+    print(f"\n[{name}/{mode}] gradient parity: " + ", ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    # the stated tolerances are for features and logits; gradients in TF32 mode go through three more chained TF32
+    # GEMMs and through ReLU masks that flip for pre-activations within TF32 error of zero, so they get 5x the budget
+    assert max(errs.values()) < (tol if mode == "fp32" else 5 * tol), errs
+    loss, correct = ctx.train_step(idx)
+    want_loss = O.cross_entropy(p, O.one_hot(lab, C)).sum()
+    assert abs(loss - want_loss) < (1e-5 if mode == "fp32" else 1e-2) * want_loss
+    assert correct == int((p.argmax(1) == lab).sum()) or mode == "tf32"
+    m, v = {k: np.zeros_like(x) for k, x in {**w, **b}.items()}, {k: np.zeros_like(x) for k, x in {**w, **b}.items()}
+    O.update_cpu_rule(w, b, gw, gb, 1e-4, "adam", m, v)
+    if mode == "fp32":
+        for l, wn in enumerate(wk):
+            assert rel_err(ctx.get_param(2 * l), w[wn]) < 1e-4, wn
+
+
 def test_streamed_image_step_equals_resident_step(lib, ctx):
     """train_step_images (H2D + extractor + step) == dataset_extract + train_step on the same batch."""
     S, C, layers, bs = 32, 10, [64, 32], 256
