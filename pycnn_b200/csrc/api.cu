@@ -964,20 +964,35 @@ int pycnn_b200_train_epoch(pycnn_b200_ctx* c, const int64_t* perm, int64_t n, in
   CTX_GUARD(c);
   PB_CHECK(c->d_params && c->d_feat, "network and dataset must be set first");
   PB_CHECK(n > 0 && batch_size > 0 && perm, "empty epoch");
-  PB_TRY(check_idx_host(c, perm, n));
   const int W = c->world, R = c->rank;
   const int64_t per_rank_max = ceil_div(std::min<int64_t>(batch_size, n), W);
   PB_TRY(ensure_workspace(c, per_rank_max));
-  PB_TRY(ensure_idx(c, n));
-  PB_CUDA(cudaMemcpyAsync(c->d_idx, perm, sizeof(int64_t) * n, cudaMemcpyHostToDevice, c->stream));
-  PB_TRY(zero_stats(c));
-  PB_TRY(reset_cursor(c));
+  // one host pass: validate and compact THIS rank's slice of every batch into pinned staging, then a single
+  // asynchronous H2D copy -- the first step's graph is enqueued right behind it
+  const int64_t num_batches = ceil_div(n, batch_size);
+  PB_TRY(ensure_pinned(c, sizeof(int64_t) * (size_t)(num_batches * per_rank_max)));
+  int64_t* h_idx = static_cast<int64_t*>(c->h_pinned);
+  int64_t k = 0;
   for (int64_t start = 0; start < n; start += batch_size) {   // pycnn/pycnn.py:626-627
     const int64_t end = std::min<int64_t>(start + batch_size, n);
     const int64_t len = end - start, per = ceil_div(len, W);
     const int64_t lo = std::min(len, per * R), hi = std::min(len, per * (R + 1));
+    for (int64_t i = start + lo; i < start + hi; ++i) {
+      const int64_t v = perm[i];
+      PB_CHECK(v >= 0 && v < c->n_rows, "row index %lld out of range [0,%lld)", (long long)v, (long long)c->n_rows);
+      h_idx[k++] = v;
+    }
+  }
+  PB_TRY(ensure_idx(c, std::max<int64_t>(k, 1)));
+  if (k > 0) PB_CUDA(cudaMemcpyAsync(c->d_idx, h_idx, sizeof(int64_t) * (size_t)k, cudaMemcpyHostToDevice, c->stream));
+  PB_TRY(zero_stats(c));
+  PB_TRY(reset_cursor(c));
+  for (int64_t start = 0; start < n; start += batch_size) {
+    const int64_t end = std::min<int64_t>(start + batch_size, n);
+    const int64_t len = end - start, per = ceil_div(len, W);
+    const int64_t lo = std::min(len, per * R), hi = std::min(len, per * (R + 1));
     const int bs = (int)(hi - lo);
-    PB_TRY(graphed_step_rows(c, bs, lo, len));   // one graph per distinct (local bs, offset, batch length)
+    PB_TRY(graphed_step_rows(c, bs, 0, bs));   // one graph per distinct local batch size
     if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += 1;
   }
   PB_TRY(read_stats(c, loss_sum, correct, true));

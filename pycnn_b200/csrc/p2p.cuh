@@ -53,13 +53,20 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// bounded spin: ~2^26 polls of a remote-written flag (seconds); a lost peer traps instead of hanging the GPU
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// bounded spin on a flag a peer writes into MY memory: relaxed polls (cheap), one acquire once it flipped;
+// ~2^26 polls (seconds) and a lost peer traps instead of hanging the GPU
 __device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long seq) {
   unsigned int polls = 0;
-  while (ld_acquire_sys(p) < seq) {
-    if (++polls > 64u) __nanosleep(32);
+  while (ld_relaxed_sys(p) < seq) {
+    if (++polls > 256u) __nanosleep(20);
     if (polls > (1u << 26)) __trap();
   }
+  (void)ld_acquire_sys(p);
 }
 // Gradients of other ranks change every step at the same addresses: never read them through the non-coherent
 // path or a possibly stale L1 line -- volatile loads go to L2 / across NVLink every time.
@@ -93,14 +100,28 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chun
     const int64_t n4 = ch.len >> 2;
     float4* mine = reinterpret_cast<float4*>(t.grads[t.rank] + ch.off);
     float acc = 0.f;
-    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < t.world; ++r) {          // fixed order: the sum is bit-identical run to run
-        const float4 v = ld_peer(reinterpret_cast<const float4*>(t.grads[r] + ch.off) + i);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    // all remote loads of a pass are issued before the first add: one NVLink round trip per pass, not one per rank
+    for (int64_t i0 = threadIdx.x; i0 < n4; i0 += 2 * blockDim.x) {
+      float4 v[2][MAX_RANKS];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int64_t i = i0 + e * (int64_t)blockDim.x;
+#pragma unroll
+        for (int r = 0; r < MAX_RANKS; ++r)
+          if (r < t.world && i < n4) v[e][r] = ld_peer(reinterpret_cast<const float4*>(t.grads[r] + ch.off) + i);
       }
-      mine[i] = s;
-      acc = fmaf(s.x, s.x, acc); acc = fmaf(s.y, s.y, acc); acc = fmaf(s.z, s.z, acc); acc = fmaf(s.w, s.w, acc);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int64_t i = i0 + e * (int64_t)blockDim.x;
+        if (i < n4) {
+          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int r = 0; r < MAX_RANKS; ++r)          // fixed rank order: the sum is bit-identical run to run
+            if (r < t.world) { s.x += v[e][r].x; s.y += v[e][r].y; s.z += v[e][r].z; s.w += v[e][r].w; }
+          mine[i] = s;
+          acc = fmaf(s.x, s.x, acc); acc = fmaf(s.y, s.y, acc); acc = fmaf(s.z, s.z, acc); acc = fmaf(s.w, s.w, acc);
+        }
+      }
     }
     const double d = warp_sum_d((double)acc);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = d;
