@@ -6,6 +6,7 @@
 #include "elementwise.cuh"
 #include "extract_tc.cuh"
 #include "gemm_tc.cuh"
+#include "mlp_tail.cuh"
 #include "p2p.cuh"
 #include "simt.cuh"
 
@@ -189,6 +190,54 @@ int forward_logits(pycnn_b200_ctx* c, const float* x, int bs) {
 }
 
 // logits live in c->d_probs.  train: writes dZ, accumulates loss/#correct and db_o, does the step bookkeeping.
+// ---- fused MLP tail (mlp_tail.cuh): layer-1 fix-up + layers 2..L+1 + softmax/CE/dZ in one launch --------------
+bool tail_supported(const pycnn_b200_ctx* c) {
+  if (c->math_mode != PYCNN_B200_MATH_TF32 || !c->use_tail || c->L < 1 || c->L > tail::MAX_TAIL) return false;
+  if (c->C > tail::MAX_C) return false;
+  if (c->dims[1] > tail::MAX_W) return false;
+  for (int l = 2; l <= c->L; ++l)
+    if (c->dims[l] > tail::MAX_N) return false;
+  return true;
+}
+
+// z1 (raw layer-1 accumulations, no bias) is in d_act[0]; leaves a1..aL in d_act, dZ_out in d_dz[L], loss/#correct
+// in d_stats and db_o in the gradient buffer (which must already be zero)
+int tail_forward_train(pycnn_b200_ctx* c, int bs, const int32_t* labels, int64_t advance) {
+  tail::TailArgs t{};
+  t.bs = bs; t.nl = c->L;                      // tail layers = hidden layers 2..L plus the output layer
+  CUtensorMap maps[1 + tail::MAX_TAIL];
+  PB_TRY(make_map_kmajor(c, &maps[0], c->d_act[0], bs, c->dims[1], c->ldw[1], 128));
+  for (int j = 0; j < t.nl; ++j) {
+    const int l = j + 1;                       // network layer index of tail layer j
+    t.K[j] = (int)c->dims[l]; t.N[j] = (int)c->dims[l + 1];
+    t.bias[j] = c->d_params + c->tensors[2 * l + 1].off;
+    t.act_out[j] = (l < c->L) ? c->d_act[l] : nullptr;
+    t.ld_out[j] = c->ldw[l + 1];
+    const TensorDesc& w = c->tensors[2 * l];
+    PB_TRY(make_map_kmajor(c, &maps[1 + j], c->d_params + w.off, w.rows, w.cols, w.ld, (int)round_up(w.rows, 16)));
+  }
+  for (int j = t.nl; j < tail::MAX_TAIL; ++j) maps[1 + j] = maps[1];
+  t.fuse_fixup = 1;
+  t.bias0 = c->d_params + c->tensors[1].off;
+  t.a_in = c->d_act[0]; t.ld_in = c->ldw[1];
+  t.labels = labels;
+  t.dz = c->d_dz[c->L]; t.ld_dz = c->ldw[c->L + 1];
+  t.stats = c->d_stats;
+  t.db_out = c->d_grads + c->tensors[2 * c->L + 1].off;
+  t.bk = StepBookkeeping{c->d_norm2, (int)c->tensors.size(), c->d_cursor, advance};
+  LaunchScope ls(c, KC_GEMM_FWD);
+  const dim3 grid((unsigned)ceil_div(bs, 128)), block(tail::THREADS);
+  const size_t smem = (size_t)tail::SMEM_BYTES;
+  const int64_t cpad = c->ldw[c->L + 1];        // pad4(C): the dZ row pitch must fit in the register tile too
+  if (cpad <= 16)
+    PB_CUDA(launch_pdl(c, tail::mlp_tail_forward_kernel<16>, grid, block, smem, c->stream, maps[0], maps[1], maps[2], maps[3], maps[4], t));
+  else if (cpad <= 32)
+    PB_CUDA(launch_pdl(c, tail::mlp_tail_forward_kernel<32>, grid, block, smem, c->stream, maps[0], maps[1], maps[2], maps[3], maps[4], t));
+  else
+    PB_CUDA(launch_pdl(c, tail::mlp_tail_forward_kernel<64>, grid, block, smem, c->stream, maps[0], maps[1], maps[2], maps[3], maps[4], t));
+  return 0;
+}
+
 int softmax_ce(pycnn_b200_ctx* c, int bs, const int32_t* labels, bool write_probs, bool write_dz, bool write_pred,
                bool stats, bool train = false, int64_t advance = 0) {
   LaunchScope ls(c, KC_SOFTMAX_CE);
@@ -324,10 +373,21 @@ int p2p_exchange_update(pycnn_b200_ctx* c) {
 // full step on x [bs, Dp] + labels (device).  bs may be 0 on a rank whose slice is empty.
 int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int bs, bool update, int64_t advance = 0) {
   if (bs > 0) {
-    PB_TRY(forward_logits(c, x, bs));
     PB_TRY(zero_grads(c));
-    // probs are not written during training; dZ goes to its own buffer
-    PB_TRY(softmax_ce(c, bs, labels, false, true, false, true, true, advance));
+    if (tail_supported(c)) {
+      // layer 1 as a raw (bias-free) GEMM, everything after it in one fused kernel
+      GemmCall g{};
+      g.A = x; g.lda = c->ldw[0]; g.a_kmajor = true;
+      g.B = c->d_params + Wt(c, 0).off; g.ldb = Wt(c, 0).ld; g.b_kmajor = true;
+      g.C = c->d_act[0]; g.ldc = c->ldw[1];
+      g.M = bs; g.N = (int)c->dims[1]; g.K = (int)c->dims[0]; g.epi = 0; g.cls = KC_GEMM_FWD1;
+      PB_TRY(gemm(c, g));
+      PB_TRY(tail_forward_train(c, bs, labels, advance));
+    } else {
+      PB_TRY(forward_logits(c, x, bs));
+      // probs are not written during training; dZ goes to its own buffer
+      PB_TRY(softmax_ce(c, bs, labels, false, true, false, true, true, advance));
+    }
     PB_TRY(backward(c, x, bs));
   } else {   // empty shard on this rank: contribute zero gradients, still advance the cursor
     PB_TRY(zero_grads(c));
@@ -542,6 +602,11 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
 #undef CREATE_CUDA
   { const char* g = getenv("PYCNN_B200_GRAPHS"); if (g && g[0] == '0') c->use_graphs = false; }
   { const char* g = getenv("PYCNN_B200_PDL"); if (g && g[0] == '0') c->use_pdl = false; }
+  { const char* g = getenv("PYCNN_B200_FUSED_TAIL"); if (g) c->use_tail = (g[0] == '1'); }
+  { cudaError_t e = cudaFuncSetAttribute(tail::mlp_tail_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail::mlp_tail_forward_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail::mlp_tail_forward_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
+    if (e != cudaSuccess) { fail("cudaFuncSetAttribute(mlp_tail) failed: %s", cudaGetErrorString(e)); return bail(1); } }
   if (tc_gemm_prepare(c) != 0 || tc_extract_prepare(c) != 0) return bail(1);
   if (resolve_encode_tiled(c) != 0) return bail(1);
   *out = c;

@@ -214,6 +214,7 @@ struct pycnn_b200_ctx {
   };
   std::map<std::tuple<int, int64_t, int64_t, int64_t, int>, GraphEntry> graphs;
   bool use_graphs = true;
+  bool use_tail = false;         // fused MLP-tail forward kernel (mlp_tail.cuh), opt-in: PYCNN_B200_FUSED_TAIL=1
   bool use_pdl = true;           // programmatic dependent launch between the step's kernels (PYCNN_B200_PDL=0 disables)
   int64_t* d_cursor = nullptr;   // [0] offset into d_idx of the current batch, [1] completed steps (device-side t)
 };

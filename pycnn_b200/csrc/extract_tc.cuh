@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(128 * MAX_WG, 1) extract_tc_kernel(const __gri
       const uint32_t py = fdiv(p, a.div_pw), px = p - py * a.PW;
       pix = img * SS + 2u * py * a.S + 2u * px;
     }
-    tc::mbar_wait(&raw_full[s], ph);
+    tc::mbar_wait_sleepy(&raw_full[s], ph);
     if (valid && !(a.debug & 2)) {
       const uint2 info = my_span[s];
       const uint32_t* words = reinterpret_cast<const uint32_t*>(raw + s * a.raw_bytes);
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(128 * MAX_WG, 1) extract_tc_kernel(const __gri
     __syncwarp();
     // ---- epilogue: thread m owns pooled position r; lanes of a warp = consecutive positions
     float* o = a.out + (int64_t)img * a.ld + p;
-    tc::mbar_wait(mma_done, it & 1);
+    tc::mbar_wait_sleepy(mma_done, it & 1);
     tc::fence_after_thread_sync();
     // 16 accumulator columns per tcgen05.ld = 4 filters x 4 pool quadrants.  Per filter: two 3-input max
     // (FMNMX3: quadrant max, then ReLU folded in), one FMUL by the per-filter scale (one LDS.128 per chunk),

@@ -53,7 +53,17 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
+// Latency-critical wait (GEMM / fused-tail hand-offs): plain try_wait polls, nothing sleeps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++polls > (1u << 24)) __trap();
+  }
+}
+// Throughput-oriented wait (persistent extractor, 16 warps per SM share the issue slots): a suspend-time hint
+// compiles to NANOSLEEP.SYNCS <hint>, which keeps waiting warps out of the schedulers' way at the price of up to
+// <hint> ns of extra latency per hand-off.
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t polls = 0;
   while (!mbar_try_wait_hint(bar, parity, 2000u)) {
