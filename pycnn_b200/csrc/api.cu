@@ -1086,6 +1086,27 @@ int pycnn_b200_train_step_images(pycnn_b200_ctx* c, const uint8_t* images, const
   return 0;
 }
 
+// two staging slots (uint8 images + labels) + their events for copy-stream || compute-stream pipelines
+static int ensure_stream_slots(pycnn_b200_ctx* c, int64_t image_bytes, int64_t num_labels) {
+  const size_t need_img = (size_t)round_up(image_bytes + 256, 1 << 20), need_lab = (size_t)round_up(std::max<int64_t>(num_labels, 1), 1024);
+  if (need_img <= c->img2_cap && need_lab <= c->lab2_cap) return 0;
+  PB_CUDA(cudaStreamSynchronize(c->stream));
+  PB_CUDA(cudaStreamSynchronize(c->copy_stream));
+  drop_graphs(c);
+  const size_t img_cap = std::max(need_img, c->img2_cap), lab_cap = std::max(need_lab, c->lab2_cap);
+  for (int s = 0; s < 2; ++s) {
+    free_dev(c->d_img2[s]); free_dev(c->d_lab2[s]);
+    c->d_img2[s] = nullptr; c->d_lab2[s] = nullptr;
+    PB_CUDA(cudaMalloc(&c->d_img2[s], img_cap));
+    PB_CUDA(cudaMemset(c->d_img2[s], 0, img_cap));
+    PB_CUDA(cudaMalloc(&c->d_lab2[s], sizeof(int32_t) * lab_cap));
+    if (!c->ev_copy[s]) PB_CUDA(cudaEventCreateWithFlags(&c->ev_copy[s], cudaEventDisableTiming));
+    if (!c->ev_compute[s]) PB_CUDA(cudaEventCreateWithFlags(&c->ev_compute[s], cudaEventDisableTiming));
+  }
+  c->img2_cap = img_cap; c->lab2_cap = lab_cap;
+  return 0;
+}
+
 static bool host_ptr_is_device_visible(const void* p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -1106,23 +1127,7 @@ int pycnn_b200_train_epoch_images(pycnn_b200_ctx* c, const uint8_t* images, cons
   const int64_t per_rank_max = ceil_div(std::min<int64_t>(batch_size, n), W);
   const int64_t num_steps = ceil_div(n, batch_size);
   PB_TRY(ensure_workspace(c, per_rank_max));
-  // staging: two slots, 16-byte aligned rows are not required by the extractor (it re-aligns its spans)
-  const size_t need_img = (size_t)round_up(per_rank_max * img_bytes + 256, 1 << 20), need_lab = (size_t)round_up(per_rank_max, 1024);
-  if (need_img > c->img2_cap || need_lab > c->lab2_cap) {
-    PB_CUDA(cudaStreamSynchronize(c->stream));
-    PB_CUDA(cudaStreamSynchronize(c->copy_stream));
-    drop_graphs(c);
-    for (int s = 0; s < 2; ++s) {
-      free_dev(c->d_img2[s]); free_dev(c->d_lab2[s]);
-      c->d_img2[s] = nullptr; c->d_lab2[s] = nullptr;
-      PB_CUDA(cudaMalloc(&c->d_img2[s], need_img));
-      PB_CUDA(cudaMemset(c->d_img2[s], 0, need_img));
-      PB_CUDA(cudaMalloc(&c->d_lab2[s], sizeof(int32_t) * need_lab));
-      if (!c->ev_copy[s]) PB_CUDA(cudaEventCreateWithFlags(&c->ev_copy[s], cudaEventDisableTiming));
-      if (!c->ev_compute[s]) PB_CUDA(cudaEventCreateWithFlags(&c->ev_compute[s], cudaEventDisableTiming));
-    }
-    c->img2_cap = need_img; c->lab2_cap = need_lab;
-  }
+  PB_TRY(ensure_stream_slots(c, per_rank_max * img_bytes, per_rank_max));
   if ((size_t)(2 * num_steps) > c->step_stats_cap) {
     if (c->h_step_stats) PB_CUDA(cudaFreeHost(c->h_step_stats));
     c->h_step_stats = nullptr;
@@ -1274,18 +1279,36 @@ int pycnn_b200_predict_images(pycnn_b200_ctx* c, const uint8_t* images, int64_t 
   PB_CHECK(feature_count(c, S) == c->D, "image_size %d with %d filters gives %lld features, network expects %lld", S, c->F, (long long)feature_count(c, S), (long long)c->D);
   const size_t img_bytes = (size_t)S * S * 3;
   const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(16384, (int64_t)(1ull << 30) / (c->Dp * 4)));
-  for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+  if (n == 0) return 0;
+  PB_TRY(ensure_workspace(c, std::min<int64_t>(chunk, n)));
+  PB_TRY(ensure_stream_slots(c, std::min<int64_t>(chunk, n) * (int64_t)img_bytes, 1));
+  // double-buffered: the H2D copy of chunk i+1 (copy stream) is enqueued BEFORE chunk i's compute and result
+  // read-back (which blocks the host for pageable destinations), so it overlaps both
+  const int64_t nchunks = ceil_div(n, chunk);
+  auto enqueue_copy = [&](int64_t ci) -> int {
+    const int64_t i0 = ci * chunk;
     const int nb = (int)std::min(chunk, n - i0);
-    PB_TRY(ensure_workspace(c, nb));
-    PB_TRY(ensure_images(c, nb * img_bytes, 0));
-    PB_CUDA(cudaMemcpyAsync(c->d_images, images + i0 * img_bytes, nb * img_bytes, cudaMemcpyHostToDevice, c->stream));
-    PB_TRY(extract_device(c, c->d_images, nb, S, c->d_x, c->Dp));
+    const int slot = (int)(ci & 1);
+    if (ci >= 2) PB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_compute[slot], 0));
+    PB_CUDA(cudaMemcpyAsync(c->d_img2[slot], images + i0 * img_bytes, nb * img_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    PB_CUDA(cudaEventRecord(c->ev_copy[slot], c->copy_stream));
+    return 0;
+  };
+  PB_TRY(enqueue_copy(0));
+  for (int64_t ci = 0; ci < nchunks; ++ci) {
+    const int64_t i0 = ci * chunk;
+    const int nb = (int)std::min(chunk, n - i0);
+    const int slot = (int)(ci & 1);
+    PB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[slot], 0));
+    PB_TRY(extract_device(c, c->d_img2[slot], nb, S, c->d_x, c->Dp));
+    PB_CUDA(cudaEventRecord(c->ev_compute[slot], c->stream));   // the staging slot is free once the extractor has read it
+    if (ci + 1 < nchunks) PB_TRY(enqueue_copy(ci + 1));
     PB_TRY(forward_logits(c, c->d_x, nb));
     PB_TRY(softmax_ce(c, nb, nullptr, false, false, true, false));
     PB_CUDA(cudaMemcpyAsync(classes + i0, c->d_pred, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, c->stream));
     if (confidences) PB_CUDA(cudaMemcpyAsync(confidences + i0, c->d_conf, sizeof(float) * nb, cudaMemcpyDeviceToHost, c->stream));
-    PB_CUDA(cudaStreamSynchronize(c->stream));
   }
+  PB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
