@@ -266,7 +266,12 @@ int zero_grads(pycnn_b200_ctx* c) {
   return 0;
 }
 
+// The critical path of the backward pass is dZ_L -> dA chain -> dZ_1 -> dW_1; the shallow dW_l (l >= 1) only need
+// dZ_l and the stored activations, so they are forked onto a side stream as soon as their dZ exists and joined
+// before the gradient exchange / update.  (While per-kernel timing is on everything stays on one stream.)
 int backward(pycnn_b200_ctx* c, const float* x, int bs) {
+  const bool fork = !c->timing && c->side_stream != nullptr && c->L >= 1 && c->L < 8;
+  cudaStream_t main_stream = c->stream;
   for (int l = c->L; l >= 0; --l) {
     const float* in = (l == 0) ? x : c->d_act[l - 1];
     const int out_n = (int)c->dims[l + 1], in_n = (int)c->dims[l];
@@ -277,7 +282,16 @@ int backward(pycnn_b200_ctx* c, const float* x, int bs) {
       g.C = c->d_grads + Wt(c, l).off; g.ldc = Wt(c, l).ld;
       g.M = out_n; g.N = in_n; g.K = bs; g.epi = 0; g.cls = (l == 0) ? KC_GEMM_DW1 : KC_GEMM_DW;
       g.c_is_zero = true;
-      PB_TRY(gemm(c, g));
+      if (fork && l > 0) {
+        PB_CUDA(cudaEventRecord(c->ev_fork[l], main_stream));
+        PB_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork[l], 0));
+        c->stream = c->side_stream;
+        const int rc = gemm(c, g);
+        c->stream = main_stream;
+        PB_TRY(rc);
+      } else {
+        PB_TRY(gemm(c, g));
+      }
     }
     if (l > 0) {  // dZ_{l-1} = (dZ_l . W_l) masked by act_{l-1} > 0 (backward_pass.pyx:85-86,97); db_{l-1} = colsum (:93)
       GemmCall g{};
@@ -290,6 +304,10 @@ int backward(pycnn_b200_ctx* c, const float* x, int bs) {
       g.cls = KC_GEMM_DA;
       PB_TRY(gemm(c, g));
     }
+  }
+  if (fork) {   // join: everything the side stream did is ordered before the exchange / update
+    PB_CUDA(cudaEventRecord(c->ev_join, c->side_stream));
+    PB_CUDA(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
   }
   return 0;
 }
@@ -591,6 +609,9 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
 #define CREATE_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { fail("%s failed: %s", #expr, cudaGetErrorString(_e)); return bail(1); } } while (0)
   CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+  for (auto& ev : c->ev_fork) CREATE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (auto& ev : c->events) CREATE_CUDA(cudaEventCreate(&ev));
   CREATE_CUDA(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming));
@@ -602,6 +623,7 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
 #undef CREATE_CUDA
   { const char* g = getenv("PYCNN_B200_GRAPHS"); if (g && g[0] == '0') c->use_graphs = false; }
   { const char* g = getenv("PYCNN_B200_PDL"); if (g && g[0] == '0') c->use_pdl = false; }
+  { const char* g = getenv("PYCNN_B200_FORK"); if (g && g[0] == '0') { cudaStreamDestroy(c->side_stream); c->side_stream = nullptr; } }
   { const char* g = getenv("PYCNN_B200_FUSED_TAIL"); if (g) c->use_tail = (g[0] == '1'); }
   { cudaError_t e = cudaFuncSetAttribute(tail::mlp_tail_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tail::mlp_tail_forward_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
@@ -641,6 +663,9 @@ int pycnn_b200_destroy(pycnn_b200_ctx* c) {
   if (c->copy_done) cudaEventDestroy(c->copy_done);
   if (c->compute_done) cudaEventDestroy(c->compute_done);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
+  for (auto& ev : c->ev_fork) if (ev) cudaEventDestroy(ev);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;

@@ -107,6 +107,8 @@ struct pycnn_b200_ctx {
   size_t l2_bytes = 0;
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // H2D staging for streamed batches
+  cudaStream_t side_stream = nullptr;  // backward: the shallow dW GEMMs run beside the dA chain (fork/join inside the graph)
+  cudaEvent_t ev_fork[8] = {}, ev_join = nullptr;
   cudaEvent_t events[16] = {};
   cudaEvent_t copy_done = nullptr, compute_done = nullptr;
   int math_mode = PYCNN_B200_MATH_TF32;
