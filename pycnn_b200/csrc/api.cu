@@ -68,6 +68,8 @@ int gemm(pycnn_b200_ctx* c, const GemmCall& g) {
 void free_workspace(pycnn_b200_ctx* c) {
   free_dev(c->d_blabels); c->d_blabels = nullptr;
   free_dev(c->d_x); c->d_x = nullptr;
+  free_dev(c->d_x2); c->d_x2 = nullptr;
+  free_dev(c->d_blabels2); c->d_blabels2 = nullptr;
   for (auto p : c->d_act) free_dev(p);
   for (auto p : c->d_dz) free_dev(p);
   c->d_act.clear(); c->d_dz.clear();
@@ -95,6 +97,15 @@ int ensure_workspace(pycnn_b200_ctx* c, int64_t bs) {
   PB_CUDA(cudaMalloc(&c->d_pred, sizeof(int32_t) * cap));
   PB_CUDA(cudaMalloc(&c->d_conf, sizeof(float) * cap));
   c->bs_cap = cap;
+  return 0;
+}
+
+// second batch buffer for the row-gather prefetch (same capacity as d_x); only the row-training entry points need it
+int ensure_prefetch_buffers(pycnn_b200_ctx* c) {
+  if (c->d_x2 || c->bs_cap == 0) return 0;
+  PB_CUDA(cudaMalloc(&c->d_blabels2, sizeof(int32_t) * c->bs_cap));
+  PB_CUDA(cudaMemset(c->d_blabels2, 0, sizeof(int32_t) * c->bs_cap));
+  PB_TRY(alloc_f32(&c->d_x2, c->bs_cap * c->Dp));
   return 0;
 }
 
@@ -170,6 +181,8 @@ int extract_device(pycnn_b200_ctx* c, const uint8_t* d_images, int64_t n, int S,
 const TensorDesc& Wt(const pycnn_b200_ctx* c, int l) { return c->tensors[2 * l]; }
 const TensorDesc& Bt(const pycnn_b200_ctx* c, int l) { return c->tensors[2 * l + 1]; }
 
+int issue_prefetch(pycnn_b200_ctx* c);
+
 // x: [bs, Dp].  Leaves hidden activations in d_act and logits in d_probs (pitch ldw[L+1]).
 int forward_logits(pycnn_b200_ctx* c, const float* x, int bs) {
   const float* in = x;
@@ -184,6 +197,7 @@ int forward_logits(pycnn_b200_ctx* c, const float* x, int bs) {
     else          { g.C = c->d_probs;  g.epi = 1; }
     g.ldc = c->ldw[l + 1];
     PB_TRY(gemm(c, g));
+    if (l == 0) PB_TRY(issue_prefetch(c));   // no-op unless a pipelined training step armed it
     in = g.C;
   }
   return 0;
@@ -388,6 +402,45 @@ int p2p_exchange_update(pycnn_b200_ctx* c) {
   return 0;
 }
 
+int gather_batch(pycnn_b200_ctx* c, const int64_t* d_idx, const int64_t* cursor, int64_t extra, int bs, float* x,
+                 int32_t* blabels);
+
+// Row-gather prefetch: as soon as the layer-1 forward GEMM (the one L2/HBM-heavy kernel of the forward pass) is
+// done, the NEXT step's rows are gathered into the other batch buffer on pf_stream -- beside the latency-bound MLP
+// tail, softmax and dA chain -- and joined at the end of the step.  In this mode nothing on the main stream reads
+// the row cursor, so the prefetch branch owns it: rows come from idx[cursor + bs ...) and the cursor moves on
+// behind the gather.
+int issue_prefetch(pycnn_b200_ctx* c) {
+  if (!c->pf.armed || c->pf.next_bs == 0) return 0;
+  c->pf.armed = false;
+  const bool fork = !c->timing && c->pf_stream != nullptr;
+  cudaStream_t main_stream = c->stream;
+  if (fork) {
+    PB_CUDA(cudaEventRecord(c->ev_pf_fork, main_stream));
+    PB_CUDA(cudaStreamWaitEvent(c->pf_stream, c->ev_pf_fork, 0));
+    c->stream = c->pf_stream;
+  }
+  int rc = gather_batch(c, c->d_idx, c->d_cursor, c->pf.extra, c->pf.next_bs, c->pf.x, c->pf.labels);
+  if (!rc) {
+    LaunchScope ls(c, KC_MISC);
+    advance_cursor_kernel<<<1, 32, 0, c->stream>>>(c->d_cursor, c->pf.extra);
+    if (cudaGetLastError() != cudaSuccess) rc = fail("advance_cursor_kernel launch failed");
+  }
+  c->stream = main_stream;
+  PB_TRY(rc);
+  c->pf.forked = fork;
+  return 0;
+}
+
+int join_prefetch(pycnn_b200_ctx* c) {
+  c->pf.armed = false;
+  if (!c->pf.forked) return 0;
+  c->pf.forked = false;
+  PB_CUDA(cudaEventRecord(c->ev_pf_join, c->pf_stream));
+  PB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_pf_join, 0));
+  return 0;
+}
+
 // full step on x [bs, Dp] + labels (device).  bs may be 0 on a rank whose slice is empty.
 int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int bs, bool update, int64_t advance = 0) {
   if (bs > 0) {
@@ -400,6 +453,7 @@ int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int 
       g.C = c->d_act[0]; g.ldc = c->ldw[1];
       g.M = bs; g.N = (int)c->dims[1]; g.K = (int)c->dims[0]; g.epi = 0; g.cls = KC_GEMM_FWD1;
       PB_TRY(gemm(c, g));
+      PB_TRY(issue_prefetch(c));
       PB_TRY(tail_forward_train(c, bs, labels, advance));
     } else {
       PB_TRY(forward_logits(c, x, bs));
@@ -413,6 +467,7 @@ int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int 
     StepBookkeeping bk{c->d_norm2, (int)c->tensors.size(), c->d_cursor, advance};
     step_bookkeeping_kernel<<<1, 256, 0, c->stream>>>(bk);
     PB_CUDA(cudaGetLastError());
+    PB_TRY(issue_prefetch(c));
   }
   if (update) {
     if (c->p2p) {
@@ -426,12 +481,19 @@ int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int 
 }
 
 // rows d_idx[*cursor + extra ...] (cursor may be null: offset 0)
-int gather_batch(pycnn_b200_ctx* c, const int64_t* d_idx, const int64_t* cursor, int64_t extra, int bs) {
+int gather_batch(pycnn_b200_ctx* c, const int64_t* d_idx, const int64_t* cursor, int64_t extra, int bs,
+                 float* x, int32_t* blabels) {
   if (bs == 0) return 0;
+  if (!x) { x = c->d_x; blabels = c->d_blabels; }
   LaunchScope ls(c, KC_GATHER);
   const int64_t total = (int64_t)bs * (c->Dp >> 2);
-  PB_CUDA(launch_pdl(c, gather_rows_kernel, dim3(grid_for(total, 256, c->num_sms)), dim3(256), 0, c->stream, c->d_feat,
-                     c->d_labels, d_idx, cursor, extra, bs, c->Dp, c->d_x, c->d_blabels));
+  // 4 loads in flight per thread; on the prefetch stream only 2 CTAs per SM so that the critical path's GEMM CTAs
+  // (one per SM, shared-memory bound) always find thread slots beside it
+  const int64_t want = ceil_div(total, 256 * 4);
+  const int per_sm = (c->stream == c->pf_stream) ? c->pf_ctas_per_sm : 8;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)per_sm * c->num_sms));
+  PB_CUDA(launch_pdl(c, gather_rows_kernel, dim3(blocks), dim3(256), 0, c->stream, c->d_feat,
+                     c->d_labels, d_idx, cursor, extra, bs, c->Dp, x, blabels));
   return 0;
 }
 
@@ -473,14 +535,34 @@ int run_graphed(pycnn_b200_ctx* c, std::tuple<int, int64_t, int64_t, int64_t, in
   return 0;
 }
 
-enum GraphKind { GK_STEP_ROWS = 1, GK_STEP_IMAGES = 2 };
+enum GraphKind { GK_STEP_ROWS = 1, GK_STEP_IMAGES = 2, GK_STEP_ROWS_PF = 3 };
 
 // one training step on dataset rows d_idx[*cursor + lo .. +bs), then cursor += advance
 int graphed_step_rows(pycnn_b200_ctx* c, int bs, int64_t lo, int64_t advance) {
   return run_graphed(c, std::make_tuple((int)GK_STEP_ROWS, (int64_t)bs, lo, advance, 0), [&]() -> int {
-    PB_TRY(gather_batch(c, c->d_idx, c->d_cursor, lo, bs));
+    PB_TRY(gather_batch(c, c->d_idx, c->d_cursor, lo, bs, nullptr, nullptr));
     PB_TRY(step_on_batch(c, c->d_x, c->d_blabels, bs, true, advance));
     return 0;
+  });
+}
+
+// Pipelined variant for runs of consecutive steps: this step's rows are already in batch buffer `parity` (gathered
+// by the previous step, or by prime_rows for the first one); while it runs, next_bs rows of the following step are
+// gathered into the other buffer.  One graph per (bs, next_bs, parity).
+float* batch_x(pycnn_b200_ctx* c, int parity) { return parity ? c->d_x2 : c->d_x; }
+int32_t* batch_labels(pycnn_b200_ctx* c, int parity) { return parity ? c->d_blabels2 : c->d_blabels; }
+
+int prime_rows(pycnn_b200_ctx* c, int bs) {   // first batch of a run -> buffer 0 (cursor already reset)
+  return gather_batch(c, c->d_idx, c->d_cursor, 0, bs, batch_x(c, 0), batch_labels(c, 0));
+}
+
+int graphed_step_rows_pf(pycnn_b200_ctx* c, int bs, int next_bs, int parity) {
+  return run_graphed(c, std::make_tuple((int)GK_STEP_ROWS_PF, (int64_t)bs, (int64_t)next_bs, (int64_t)bs, parity), [&]() -> int {
+    c->pf.armed = true; c->pf.forked = false; c->pf.next_bs = next_bs; c->pf.extra = bs;
+    c->pf.x = batch_x(c, parity ^ 1); c->pf.labels = batch_labels(c, parity ^ 1);
+    int rc = step_on_batch(c, batch_x(c, parity), batch_labels(c, parity), bs, true, 0);
+    const int rj = join_prefetch(c);
+    return rc ? rc : rj;
   });
 }
 
@@ -610,6 +692,13 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CREATE_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+  {
+    int prio_lo = 0, prio_hi = 0;   // the prefetch gather yields SM slots to the critical path
+    CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CREATE_CUDA(cudaStreamCreateWithPriority(&c->pf_stream, cudaStreamNonBlocking, prio_lo));
+  }
+  CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_pf_fork, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_pf_join, cudaEventDisableTiming));
   for (auto& ev : c->ev_fork) CREATE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (auto& ev : c->events) CREATE_CUDA(cudaEventCreate(&ev));
@@ -624,11 +713,26 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_GRAPHS"); if (g && g[0] == '0') c->use_graphs = false; }
   { const char* g = getenv("PYCNN_B200_PDL"); if (g && g[0] == '0') c->use_pdl = false; }
   { const char* g = getenv("PYCNN_B200_FORK"); if (g && g[0] == '0') { cudaStreamDestroy(c->side_stream); c->side_stream = nullptr; } }
+  { const char* g = getenv("PYCNN_B200_CARVEOUT"); if (g && g[0] == '0') c->uniform_carveout = false; }
+  { const char* g = getenv("PYCNN_B200_PF_CTAS"); if (g && atoi(g) > 0) c->pf_ctas_per_sm = atoi(g); }
+  { const char* g = getenv("PYCNN_B200_PREFETCH"); if (g && g[0] == '0') c->use_prefetch = false; }
+  { const char* g = getenv("PYCNN_B200_CLUSTER_SPLITK"); if (g && g[0] == '0') c->use_cluster_splitk = false; }
   { const char* g = getenv("PYCNN_B200_FUSED_TAIL"); if (g) c->use_tail = (g[0] == '1'); }
   { cudaError_t e = cudaFuncSetAttribute(tail::mlp_tail_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tail::mlp_tail_forward_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tail::mlp_tail_forward_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
     if (e != cudaSuccess) { fail("cudaFuncSetAttribute(mlp_tail) failed: %s", cudaGetErrorString(e)); return bail(1); } }
+  if (c->uniform_carveout) {
+    // same shared-memory carve-out as the GEMM kernels (see prepare_tc_gemm) for everything that runs beside them
+    cudaError_t e = cudaSuccess;
+    auto prefer = [&](const void* f) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    };
+    prefer((const void*)gather_rows_kernel); prefer((const void*)softmax_ce_kernel); prefer((const void*)grad_sqnorm_kernel);
+    prefer((const void*)clip_update_kernel); prefer((const void*)gemm_fixup_kernel); prefer((const void*)step_bookkeeping_kernel);
+    prefer((const void*)colsum_kernel); prefer((const void*)p2p::p2p_reduce_kernel); prefer((const void*)p2p::p2p_update_kernel);
+    if (e != cudaSuccess) { fail("cudaFuncSetAttribute(carve-out) failed: %s", cudaGetErrorString(e)); return bail(1); }
+  }
   if (tc_gemm_prepare(c) != 0 || tc_extract_prepare(c) != 0) return bail(1);
   if (resolve_encode_tiled(c) != 0) return bail(1);
   *out = c;
@@ -664,6 +768,9 @@ int pycnn_b200_destroy(pycnn_b200_ctx* c) {
   if (c->compute_done) cudaEventDestroy(c->compute_done);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->side_stream) cudaStreamDestroy(c->side_stream);
+  if (c->pf_stream) cudaStreamDestroy(c->pf_stream);
+  if (c->ev_pf_fork) cudaEventDestroy(c->ev_pf_fork);
+  if (c->ev_pf_join) cudaEventDestroy(c->ev_pf_join);
   for (auto& ev : c->ev_fork) if (ev) cudaEventDestroy(ev);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1043,7 +1150,13 @@ int pycnn_b200_train_steps(pycnn_b200_ctx* c, const int64_t* idx, int bs, int st
   PB_CUDA(cudaMemcpyAsync(c->d_idx, idx, sizeof(int64_t) * bs * steps, cudaMemcpyHostToDevice, c->stream));
   PB_TRY(zero_stats(c));
   PB_TRY(reset_cursor(c));
-  for (int s = 0; s < steps; ++s) PB_TRY(graphed_step_rows(c, bs, 0, bs));
+  if (c->use_prefetch && steps > 1) {
+    PB_TRY(ensure_prefetch_buffers(c));
+    PB_TRY(prime_rows(c, bs));
+    for (int s = 0; s < steps; ++s) PB_TRY(graphed_step_rows_pf(c, bs, s + 1 < steps ? bs : 0, s & 1));
+  } else {
+    for (int s = 0; s < steps; ++s) PB_TRY(graphed_step_rows(c, bs, 0, bs));
+  }
   if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += steps;
   if (loss_sum || correct) PB_TRY(read_stats(c, loss_sum, correct, true));
   return 0;
@@ -1077,12 +1190,23 @@ int pycnn_b200_train_epoch(pycnn_b200_ctx* c, const int64_t* perm, int64_t n, in
   if (k > 0) PB_CUDA(cudaMemcpyAsync(c->d_idx, h_idx, sizeof(int64_t) * (size_t)k, cudaMemcpyHostToDevice, c->stream));
   PB_TRY(zero_stats(c));
   PB_TRY(reset_cursor(c));
-  for (int64_t start = 0; start < n; start += batch_size) {
+  auto local_bs = [&](int64_t start) -> int {
+    if (start >= n) return 0;
     const int64_t end = std::min<int64_t>(start + batch_size, n);
     const int64_t len = end - start, per = ceil_div(len, W);
-    const int64_t lo = std::min(len, per * R), hi = std::min(len, per * (R + 1));
-    const int bs = (int)(hi - lo);
-    PB_TRY(graphed_step_rows(c, bs, 0, bs));   // one graph per distinct local batch size
+    return (int)(std::min(len, per * (R + 1)) - std::min(len, per * R));
+  };
+  const bool pipelined = c->use_prefetch && num_batches > 1;
+  if (pipelined) {
+    PB_TRY(ensure_prefetch_buffers(c));
+    PB_TRY(prime_rows(c, local_bs(0)));
+  }
+  int parity = 0;
+  for (int64_t start = 0; start < n; start += batch_size, parity ^= 1) {
+    const int bs = local_bs(start);
+    // one graph per distinct local batch size (x next size x buffer parity when the row gather is pipelined)
+    if (pipelined) PB_TRY(graphed_step_rows_pf(c, bs, local_bs(start + batch_size), parity));
+    else           PB_TRY(graphed_step_rows(c, bs, 0, bs));
     if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += 1;
   }
   PB_TRY(read_stats(c, loss_sum, correct, true));
@@ -1238,7 +1362,7 @@ int pycnn_b200_forward_backward(pycnn_b200_ctx* c, const int64_t* idx, int bs) {
     PB_TRY(ensure_workspace(c, bs));
     PB_TRY(ensure_idx(c, bs));
     PB_CUDA(cudaMemcpyAsync(c->d_idx, idx, sizeof(int64_t) * bs, cudaMemcpyHostToDevice, c->stream));
-    PB_TRY(gather_batch(c, c->d_idx, nullptr, 0, bs));
+    PB_TRY(gather_batch(c, c->d_idx, nullptr, 0, bs, nullptr, nullptr));
   }
   PB_TRY(step_on_batch(c, c->d_x, c->d_blabels, bs, false));
   PB_CUDA(cudaStreamSynchronize(c->stream));  // the external all-reduce runs on someone else's stream
@@ -1276,7 +1400,7 @@ int pycnn_b200_forward_rows(pycnn_b200_ctx* c, const int64_t* idx, int64_t row0,
     PB_TRY(check_idx_host(c, idx, bs));
     PB_TRY(ensure_idx(c, bs));
     PB_CUDA(cudaMemcpyAsync(c->d_idx, idx, sizeof(int64_t) * bs, cudaMemcpyHostToDevice, c->stream));
-    PB_TRY(gather_batch(c, c->d_idx, nullptr, 0, bs));
+    PB_TRY(gather_batch(c, c->d_idx, nullptr, 0, bs, nullptr, nullptr));
     x = c->d_x;
   } else {
     PB_CHECK(row0 >= 0 && row0 + bs <= c->n_rows, "rows [%lld,%lld) outside the dataset", (long long)row0, (long long)(row0 + bs));

@@ -109,6 +109,19 @@ struct pycnn_b200_ctx {
   cudaStream_t copy_stream = nullptr;  // H2D staging for streamed batches
   cudaStream_t side_stream = nullptr;  // backward: the shallow dW GEMMs run beside the dA chain (fork/join inside the graph)
   cudaEvent_t ev_fork[8] = {}, ev_join = nullptr;
+  cudaStream_t pf_stream = nullptr;    // gather of the NEXT step's rows, overlapped with this step's backward pass
+  cudaEvent_t ev_pf_fork = nullptr, ev_pf_join = nullptr;
+  struct Prefetch {                    // armed by graphed_step_rows_pf, consumed by step_on_batch
+    bool armed = false, forked = false;
+    int next_bs = 0;
+    int64_t extra = 0;                 // rows of the current step: the next batch starts at cursor + extra
+    float* x = nullptr;
+    int32_t* labels = nullptr;
+  } pf;
+  bool use_prefetch = true;
+  int pf_ctas_per_sm = 2;              // gather CTAs per SM on the prefetch stream (PYCNN_B200_PF_CTAS)
+  bool uniform_carveout = true;        // elementwise kernels ask for the GEMMs' L1/shared split (PYCNN_B200_CARVEOUT=0 disables)
+  bool use_cluster_splitk = true;      // split-K partials meet in distributed shared memory (PYCNN_B200_CLUSTER_SPLITK=0: global atomics)
   cudaEvent_t events[16] = {};
   cudaEvent_t copy_done = nullptr, compute_done = nullptr;
   int math_mode = PYCNN_B200_MATH_TF32;
@@ -151,6 +164,8 @@ struct pycnn_b200_ctx {
   int64_t idx_cap = 0;
   int32_t* d_blabels = nullptr;
   float* d_x = nullptr;               // gathered batch [bs, Dp]
+  float* d_x2 = nullptr;              // second batch buffer (row-gather prefetch), allocated on first use
+  int32_t* d_blabels2 = nullptr;
   std::vector<float*> d_act;          // [L] hidden activations [bs, ldw[l+1]]
   std::vector<float*> d_dz;           // [L+1] dZ per layer [bs, ldw[l+1]]
   float* d_probs = nullptr;           // [bs, ldw[L+1]]
@@ -260,20 +275,36 @@ struct LaunchScope {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// cluster_z > 0: launch as thread-block clusters of (1, 1, cluster_z)
 template <class... KArgs, class... Args>
-static inline cudaError_t launch_pdl(pycnn_b200_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                                     cudaStream_t stream, Args&&... args) {
+static inline cudaError_t launch_pdl_cluster(pycnn_b200_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                                             size_t smem, cudaStream_t stream, int cluster_z, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (c->use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster_z > 0) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = (unsigned)cluster_z;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = c->use_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(pycnn_b200_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t stream, Args&&... args) {
+  return launch_pdl_cluster(c, kernel, grid, block, smem, stream, 0, static_cast<Args&&>(args)...);
 }
 
 static inline int ensure_scratch(pycnn_b200_ctx* c, size_t bytes) {

@@ -41,6 +41,36 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
 // ---------------------------------------------------------------------------------------------
 // The batch's indices are idx_base[*cursor + extra ...]: the cursor lives on the device so that one captured
 // CUDA graph can be replayed for every batch of an epoch (advance_cursor_kernel moves it).
+template <class I>
+__device__ __forceinline__ void gather_rows_body(const float* __restrict__ feat, const int32_t* __restrict__ labels,
+                                                 const int64_t* __restrict__ idx, I total, I vec_per_row, int64_t Dp,
+                                                 float* __restrict__ x, int32_t* __restrict__ blabels) {
+  constexpr int U = 4;   // independent 128-bit loads in flight per thread: the kernel also runs with few CTAs per SM
+  const I stride = (I)gridDim.x * blockDim.x;
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride * U) {
+    float4 v[U];
+    I r[U], c[U];
+    int64_t src[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const I iu = i + (I)u * stride;
+      if (iu < total) {
+        r[u] = iu / vec_per_row; c[u] = iu - r[u] * vec_per_row;
+        src[u] = idx[r[u]];
+        v[u] = ld_stream(reinterpret_cast<const float4*>(feat + src[u] * Dp) + c[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const I iu = i + (I)u * stride;
+      if (iu < total) {
+        st_stream(reinterpret_cast<float4*>(x + (int64_t)r[u] * Dp) + c[u], v[u]);
+        if (c[u] == 0) blabels[r[u]] = labels[src[u]];
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ feat,
                                                           const int32_t* __restrict__ labels,
                                                           const int64_t* __restrict__ idx_base,
@@ -52,14 +82,10 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
   const int64_t* __restrict__ idx = idx_base + (cursor ? cursor[0] : 0) + extra;
   const int64_t vec_per_row = Dp >> 2;
   const int64_t total = (int64_t)bs * vec_per_row;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / vec_per_row, c = i - r * vec_per_row;
-    const int64_t src = idx[r];
-    const float4 v = ld_stream(reinterpret_cast<const float4*>(feat + src * Dp) + c);
-    st_stream(reinterpret_cast<float4*>(x + r * Dp) + c, v);
-    if (c == 0) blabels[r] = labels[src];
-  }
+  if (total < (int64_t)0x7fffffff - (int64_t)4 * gridDim.x * blockDim.x)
+    gather_rows_body<uint32_t>(feat, labels, idx, (uint32_t)total, (uint32_t)vec_per_row, Dp, x, blabels);
+  else
+    gather_rows_body<int64_t>(feat, labels, idx, total, vec_per_row, Dp, x, blabels);
 }
 
 // Zero-copy batch assembly: rows idx[i] of a pinned host array (device-visible through UVA) are pulled over
@@ -103,6 +129,10 @@ struct StepBookkeeping {   // per-step housekeeping folded into the softmax kern
   int64_t* cursor;         // cursor[0] += advance (next batch of the permutation); cursor[1] += 1 (step count t)
   int64_t advance;
 };
+
+__global__ void advance_cursor_kernel(int64_t* cursor, int64_t advance) {   // tail of the prefetch branch
+  if (threadIdx.x == 0) cursor[0] += advance;
+}
 
 __global__ void step_bookkeeping_kernel(StepBookkeeping bk) {   // ranks whose shard of a batch is empty
   pdl_wait();

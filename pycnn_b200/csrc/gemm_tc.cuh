@@ -51,10 +51,116 @@ struct TcGemmArgs {
   const float* mask;
   int64_t ldmask;
   float* colsum;     // optional: colsum[n] += sum_m C[m,n] of the epilogue output (bias gradient), !atomic only
+  int cluster_reduce;  // 1: gridDim.z == cluster size; the split-K partial tiles meet in distributed shared memory
 };
+
+// ---- thread-block cluster helpers (split-K reduction through distributed shared memory) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_dsmem_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Cluster split-K tail (see the kernel): CTA `rank` of S finishes rows [rank*128/S, (rank+1)*128/S) of the tile.  A warp
+// takes RG rows at a time so that RG*S = 16 remote 128-bit loads are in flight per lane (DSMEM latency is ~2x L2's).
+template <int BN, int S>
+__device__ __forceinline__ void cluster_reduce_rows(const TcGemmArgs& g, uint8_t* smem, int q, int lane, int m0, int n0) {
+  constexpr int PITCH = BN + 4;
+  constexpr int RPC = G_BM / S;        // rows per CTA: 64 / 32 / 16
+  constexpr int RPW = RPC / 4;         // rows per warp: 16 / 8 / 4
+  constexpr int RG = 16 / S;           // rows per batch: 8 / 4 / 2
+  constexpr int PASSES = (BN + 127) / 128;
+  const uint32_t rank = cluster_ctarank();
+  const int ncols = min(BN, g.N - n0);
+  const uint32_t stage_local = smem_u32(smem);
+  uint32_t stage_of[S];
+#pragma unroll
+  for (int z = 0; z < S; ++z) stage_of[z] = map_to_cta(stage_local, (uint32_t)z);
+  const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+                      (g.epi != 3 || (((g.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0)));
+#pragma unroll 1
+  for (int pass = 0; pass < PASSES; ++pass) {
+    const int cc = pass * 128 + lane * 4;
+    if (cc >= ncols) continue;
+    const int n = n0 + cc;
+    float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (g.epi == 1 || g.epi == 2) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) bias4[e] = (n + e < g.N) ? __ldg(g.bias + n + e) : 0.f;
+    }
+#pragma unroll 1
+    for (int b = 0; b < RPW; b += RG) {
+      // tile rows of this batch: rank*RPC + q*RPW + b + i   (a warp owns RPW consecutive rows)
+      const int r0 = (int)rank * RPC + q * RPW + b;
+      if ((int64_t)m0 + r0 >= g.M) break;
+      float4 part[RG][S];
+#pragma unroll
+      for (int i = 0; i < RG; ++i) {
+        const uint32_t off = (uint32_t)((r0 + i) * PITCH + cc) * 4u;
+#pragma unroll
+        for (int z = 0; z < S; ++z) part[i][z] = ld_dsmem_v4(stage_of[z] + off);
+      }
+      float mk[RG][4];
+      if (g.epi == 3) {
+#pragma unroll
+        for (int i = 0; i < RG; ++i) {
+          const int64_t grow = (int64_t)m0 + r0 + i;
+          if (grow < g.M) {
+            const float* mrow = g.mask + grow * g.ldmask + n;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) mk[i][e] = (vec_ok || n + e < g.N) ? __ldg(mrow + e) : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < RG; ++i) {
+        const int64_t grow = (int64_t)m0 + r0 + i;
+        if (grow < g.M) {
+          float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int z = 0; z < S; ++z) { o[0] += part[i][z].x; o[1] += part[i][z].y; o[2] += part[i][z].z; o[3] += part[i][z].w; }
+          if (g.epi == 1 || g.epi == 2) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] += bias4[e];
+          }
+          if (g.epi == 2) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = (o[e] < 0.f) ? 0.f : o[e];
+          }
+          if (g.epi == 3) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = (mk[i][e] <= 0.f) ? 0.f : o[e];
+          }
+          float* crow = g.C + grow * g.ldc + n;
+          if (vec_ok) {
+            *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < g.N) crow[e] = o[e];
+          }
+        }
+      }
+    }
+  }
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -171,6 +277,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
     __syncwarp();
+    if (!g.cluster_reduce) {
     const int row0 = m0 + q * 32;
     const int nrows = min(32, g.M - row0);            // warp-uniform, may be <= 0
     const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
@@ -262,6 +369,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
     }
+    }  // !cluster_reduce
+  }
+  if (g.cluster_reduce) {
+    // Split-K without global partial sums: the gridDim.z CTAs of one output tile form a thread-block cluster, each
+    // has parked its raw 128 x BN partial tile in its own shared memory (above).  After a cluster barrier CTA r sums
+    // rows [r*128/S, (r+1)*128/S) over the S partials in rank order (deterministic) straight out of its peers'
+    // shared memory, applies bias / ReLU / mask and writes the finished rows of C -- no zero-fill, no atomics, no
+    // fix-up pass.  Every thread of every CTA takes part in both barriers; the second keeps a CTA's shared memory
+    // alive until its peers are done reading it.  (A push variant -- st.shared::cluster from TMEM into the owner's
+    // smem -- measured 2.4 us slower: it needs one more cluster barrier before anyone may overwrite operand smem.)
+    cluster_sync_all();
+    if (warp >= 2) {
+      switch (cluster_nctarank()) {
+        case 2: cluster_reduce_rows<BN, 2>(g, smem, warp & 3, lane, m0, n0); break;
+        case 4: cluster_reduce_rows<BN, 4>(g, smem, warp & 3, lane, m0, n0); break;
+        default: cluster_reduce_rows<BN, 8>(g, smem, warp & 3, lane, m0, n0); break;
+      }
+    }
+    cluster_sync_all();
   }
   fence_before_thread_sync();
   __syncthreads();
@@ -338,10 +464,33 @@ struct GemmCall {
   bool c_is_zero;     // caller guarantees C is already zero (skips the split-K memset)
 };
 
+// how many clusters of S CTAs (S = 2, 4, 8 -> slot 0, 1, 2) of each instantiation the device can hold at once;
+// queried once per process, outside any stream capture
+static int g_max_clusters[4][3][3];   // [BN slot][layout slot][S slot]
+static inline int bn_slot(int BN) { return BN == 32 ? 0 : BN == 64 ? 1 : BN == 128 ? 2 : 3; }
+static inline int layout_slot(bool a_mn, bool b_mn) { return !a_mn ? (b_mn ? 1 : 0) : 2; }
+
 template <int BN, bool A_MN, bool B_MN>
 static int prepare_tc_gemm() {
-  PB_CUDA(cudaFuncSetAttribute(tc::gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               tc::GemmCfg<BN>::SMEM_BYTES));
+  auto kern = tc::gemm_tf32_kernel<BN, A_MN, B_MN>;
+  PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<BN>::SMEM_BYTES));
+  // every kernel of the training step asks for the same L1/shared split: an SM only hosts CTAs of kernels whose
+  // carve-out matches, so mixed preferences would serialise the PDL / fork-join / prefetch overlaps
+  PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  for (int si = 0; si < 3; ++si) {
+    const int S = 2 << si;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1, 64, S);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = tc::GemmCfg<BN>::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+    g_max_clusters[bn_slot(BN)][layout_slot(A_MN, B_MN)][si] = n;
+  }
   return 0;
 }
 template <bool A_MN, bool B_MN>
@@ -365,7 +514,7 @@ static int launch_tc_gemm(pycnn_b200_ctx* c, const GemmCall& g, const CUtensorMa
                           const tc::TcGemmArgs& args, dim3 grid) {
   using Cfg = tc::GemmCfg<BN>;
   auto kern = tc::gemm_tf32_kernel<BN, A_MN, B_MN>;
-  PB_CUDA(launch_pdl(c, kern, grid, dim3(192), (size_t)Cfg::SMEM_BYTES, c->stream, ma, mb, args));
+  PB_CUDA(launch_pdl_cluster(c, kern, grid, dim3(192), (size_t)Cfg::SMEM_BYTES, c->stream, args.cluster_reduce ? (int)grid.z : 0, ma, mb, args));
   return 0;
 }
 
@@ -401,6 +550,20 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   }
   int kb_per_split = (int)ceil_div(num_kb, split);
   split = (int)ceil_div(num_kb, kb_per_split);  // no empty slices
+  // When the output needs an epilogue (or is not known to be zero) the k-slices of a tile run as one thread-block
+  // cluster and meet in distributed shared memory instead of in global atomics: no zero-fill, no fix-up pass,
+  // deterministic.  Needs a cluster size of 2/4/8 with no empty slice and all clusters resident at once.
+  bool cluster = false;
+  if (split > 1 && (g.epi != 0 || !g.c_is_zero) && c->use_cluster_splitk) {
+    for (int si = 2; si >= 0 && !cluster; --si) {
+      const int S = 2 << si;
+      if (S > split) continue;
+      const int kbps = (int)ceil_div(num_kb, S);
+      if ((int)ceil_div(num_kb, kbps) != S) continue;
+      if (g_max_clusters[bn_slot(BN)][layout_slot(!g.a_kmajor, !g.b_kmajor)][si] < tiles) continue;
+      cluster = true; split = S; kb_per_split = kbps;
+    }
+  }
   CUtensorMap ma, mb;
   if (g.a_kmajor) PB_TRY(make_map_kmajor(c, &ma, g.A, g.M, g.K, g.lda, tc::G_BM));
   else            PB_TRY(make_map_mnmajor(c, &ma, g.A, g.K, g.M, g.lda));
@@ -412,8 +575,10 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   a.num_kb = num_kb; a.kb_per_split = kb_per_split;
   a.bias = g.bias; a.mask = g.mask; a.ldmask = g.ldmask;
   a.colsum = g.colsum;
+  a.cluster_reduce = cluster ? 1 : 0;
+  if (cluster) a.atomic = 0;
   dim3 grid(tiles_n, tiles_m, split);
-  if (split > 1 && !g.c_is_zero) {
+  if (split > 1 && !g.c_is_zero && !cluster) {
     LaunchScope ls(c, g.cls);   // the split-K zero-fill and fix-up are part of this GEMM's cost
     PB_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * ((size_t)(g.M - 1) * g.ldc + g.N), c->stream));
   }
@@ -423,7 +588,7 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
     else if (g.a_kmajor && !g.b_kmajor) PB_TRY((dispatch_bn<false, true>(c, BN, g, ma, mb, a, grid)));
     else PB_TRY((dispatch_bn<true, true>(c, BN, g, ma, mb, a, grid)));
   }
-  if (split > 1 && g.epi != 0) {
+  if (split > 1 && g.epi != 0 && !cluster) {
     LaunchScope ls(c, g.cls);
     const int64_t total = (int64_t)g.M * g.N;
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 8 * c->num_sms);
