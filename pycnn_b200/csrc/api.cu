@@ -183,8 +183,15 @@ const TensorDesc& Bt(const pycnn_b200_ctx* c, int l) { return c->tensors[2 * l +
 
 int issue_prefetch(pycnn_b200_ctx* c);
 
+// The output layer's GEMM can finish the training forward pass itself (softmax, CE, dZ, db_o, tallies, bookkeeping)
+bool softmax_fusable(const pycnn_b200_ctx* c) {
+  return c->fuse_softmax && c->math_mode == PYCNN_B200_MATH_TF32 && c->C <= 32;
+}
+
 // x: [bs, Dp].  Leaves hidden activations in d_act and logits in d_probs (pitch ldw[L+1]).
-int forward_logits(pycnn_b200_ctx* c, const float* x, int bs) {
+// train_labels != nullptr (only with softmax_fusable): the last GEMM runs the fused softmax/CE epilogue instead of
+// writing logits -- dZ_out lands in d_dz[L], loss/#correct in d_stats, db_o in the (zeroed) gradient buffer.
+int forward_logits(pycnn_b200_ctx* c, const float* x, int bs, const int32_t* train_labels = nullptr, int64_t advance = 0) {
   const float* in = x;
   for (int l = 0; l <= c->L; ++l) {
     GemmCall g{};
@@ -196,6 +203,12 @@ int forward_logits(pycnn_b200_ctx* c, const float* x, int bs) {
     if (l < c->L) { g.C = c->d_act[l]; g.epi = 2; }
     else          { g.C = c->d_probs;  g.epi = 1; }
     g.ldc = c->ldw[l + 1];
+    if (l == c->L && train_labels) {
+      g.epi = 4;
+      g.labels = train_labels; g.dz = c->d_dz[c->L]; g.lddz = c->ldw[c->L + 1]; g.stats = c->d_stats;
+      g.db = c->d_grads + Bt(c, c->L).off;
+      g.bk = StepBookkeeping{c->d_norm2, (int)c->tensors.size(), c->d_cursor, advance};
+    }
     PB_TRY(gemm(c, g));
     if (l == 0) PB_TRY(issue_prefetch(c));   // no-op unless a pipelined training step armed it
     in = g.C;
@@ -456,9 +469,13 @@ int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int 
       PB_TRY(issue_prefetch(c));
       PB_TRY(tail_forward_train(c, bs, labels, advance));
     } else {
-      PB_TRY(forward_logits(c, x, bs));
-      // probs are not written during training; dZ goes to its own buffer
-      PB_TRY(softmax_ce(c, bs, labels, false, true, false, true, true, advance));
+      if (softmax_fusable(c)) {
+        PB_TRY(forward_logits(c, x, bs, labels, advance));
+      } else {
+        PB_TRY(forward_logits(c, x, bs));
+        // probs are not written during training; dZ goes to its own buffer
+        PB_TRY(softmax_ce(c, bs, labels, false, true, false, true, true, advance));
+      }
     }
     PB_TRY(backward(c, x, bs));
   } else {   // empty shard on this rank: contribute zero gradients, still advance the cursor
@@ -716,6 +733,9 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_CARVEOUT"); if (g && g[0] == '0') c->uniform_carveout = false; }
   { const char* g = getenv("PYCNN_B200_PF_CTAS"); if (g && atoi(g) > 0) c->pf_ctas_per_sm = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PREFETCH"); if (g && g[0] == '0') c->use_prefetch = false; }
+  { const char* g = getenv("PYCNN_B200_FUSE_SOFTMAX"); if (g && g[0] == '0') c->fuse_softmax = false; }
+  { const char* g = getenv("PYCNN_B200_ONE_WAVE"); if (g && g[0] == '0') c->one_wave_tiles = false; }
+  { const char* g = getenv("PYCNN_B200_PAIR"); if (g && g[0] == '0') c->use_pair = false; }
   { const char* g = getenv("PYCNN_B200_CLUSTER_SPLITK"); if (g && g[0] == '0') c->use_cluster_splitk = false; }
   { const char* g = getenv("PYCNN_B200_FUSED_TAIL"); if (g) c->use_tail = (g[0] == '1'); }
   { cudaError_t e = cudaFuncSetAttribute(tail::mlp_tail_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
@@ -811,8 +831,11 @@ int pycnn_b200_device_info(pycnn_b200_ctx* c, char* buf, size_t buflen) {
   PB_CHECK(buf && buflen > 0, "null buffer");
   cudaDeviceProp prop;
   PB_CUDA(cudaGetDeviceProperties(&prop, c->device));
-  snprintf(buf, buflen, "%s sm_%d%d, %d SMs, %.1f GiB, L2 %.0f MiB", prop.name, prop.major, prop.minor,
-           prop.multiProcessorCount, prop.totalGlobalMem / 1073741824.0, prop.l2CacheSize / 1048576.0);
+  // co-resident GEMM clusters (128x256 forward tile): plain 2/4/8-CTA split-K clusters and paired (x2) ones
+  const auto& occ = g_max_clusters[3][0];
+  snprintf(buf, buflen, "%s sm_%d%d, %d SMs, %.1f GiB, L2 %.0f MiB; max resident GEMM clusters 1x{2,4,8}=%d/%d/%d 2x{1,2,4}=%d/%d/%d",
+           prop.name, prop.major, prop.minor, prop.multiProcessorCount, prop.totalGlobalMem / 1073741824.0,
+           prop.l2CacheSize / 1048576.0, occ[0][1], occ[0][2], occ[0][3], occ[1][0], occ[1][1], occ[1][2]);
   return 0;
 }
 

@@ -121,6 +121,9 @@ struct pycnn_b200_ctx {
   bool use_prefetch = true;
   int pf_ctas_per_sm = 2;              // gather CTAs per SM on the prefetch stream (PYCNN_B200_PF_CTAS)
   bool uniform_carveout = true;        // elementwise kernels ask for the GEMMs' L1/shared split (PYCNN_B200_CARVEOUT=0 disables)
+  bool fuse_softmax = true;            // training: softmax/CE/dZ in the output-layer GEMM's epilogue (PYCNN_B200_FUSE_SOFTMAX=0: own kernel)
+  bool one_wave_tiles = true;          // shallow-K GEMMs: widen the tile rather than run a second wave (PYCNN_B200_ONE_WAVE=0 disables)
+  bool use_pair = true;                // M-adjacent GEMM CTAs share the B tile by TMA multicast (PYCNN_B200_PAIR=0 disables)
   bool use_cluster_splitk = true;      // split-K partials meet in distributed shared memory (PYCNN_B200_CLUSTER_SPLITK=0: global atomics)
   cudaEvent_t events[16] = {};
   cudaEvent_t copy_done = nullptr, compute_done = nullptr;
@@ -275,10 +278,10 @@ struct LaunchScope {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// cluster_z > 0: launch as thread-block clusters of (1, 1, cluster_z)
+// launch as thread-block clusters of (1, cluster_y, cluster_z) when that is more than one CTA
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl_cluster(pycnn_b200_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block,
-                                             size_t smem, cudaStream_t stream, int cluster_z, Args&&... args) {
+                                             size_t smem, cudaStream_t stream, int cluster_y, int cluster_z, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -291,9 +294,9 @@ static inline cudaError_t launch_pdl_cluster(pycnn_b200_ctx* c, void (*kernel)(K
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (cluster_z > 0) {
+  if (cluster_y * cluster_z > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = (unsigned)cluster_z;
+    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = (unsigned)cluster_y; attr[na].val.clusterDim.z = (unsigned)cluster_z;
     ++na;
   }
   cfg.attrs = attr;
@@ -304,7 +307,7 @@ static inline cudaError_t launch_pdl_cluster(pycnn_b200_ctx* c, void (*kernel)(K
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl(pycnn_b200_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                      cudaStream_t stream, Args&&... args) {
-  return launch_pdl_cluster(c, kernel, grid, block, smem, stream, 0, static_cast<Args&&>(args)...);
+  return launch_pdl_cluster(c, kernel, grid, block, smem, stream, 1, 1, static_cast<Args&&>(args)...);
 }
 
 static inline int ensure_scratch(pycnn_b200_ctx* c, size_t bytes) {

@@ -113,7 +113,8 @@ def test_optimized_cpp_dropins(ctx):
 
 # ------------------------------------------------------------------------------------------ GEMM
 GEMM_SHAPES = [(128, 256, 64), (4096 // 8, 256, 4275), (32, 10, 64), (200, 100, 1000), (256, 4275, 512), (77, 33, 45),
-               (128, 64, 8), (300, 513, 96)]
+               (128, 64, 8), (300, 513, 96),
+               (1100, 2304, 2100)]   # deep K, odd M-tile count: paired CTAs with multicast B and a padding CTA
 
 
 @pytest.mark.parametrize("mode,tol", [("fp32", FP32_TOL), ("tf32", 2e-3)])
