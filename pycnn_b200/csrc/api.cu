@@ -183,6 +183,29 @@ const TensorDesc& Bt(const pycnn_b200_ctx* c, int l) { return c->tensors[2 * l +
 
 int issue_prefetch(pycnn_b200_ctx* c);
 
+// Gradient buffers are zeroed once per step: split-K dW partial sums and the fused bias-gradient column sums
+// (output-layer epilogue / softmax kernel, dA-GEMM epilogues) accumulate into them.  Inside a training step the
+// memset runs on the side stream beside the hidden-layer forward GEMMs and is joined before the first writer.
+int zero_grads(pycnn_b200_ctx* c, bool may_fork = false) {
+  LaunchScope ls(c, KC_MISC);
+  if (may_fork && !c->timing && c->side_stream) {
+    PB_CUDA(cudaEventRecord(c->ev_fork[0], c->stream));
+    PB_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork[0], 0));
+    PB_CUDA(cudaMemsetAsync(c->d_grads, 0, sizeof(float) * c->P, c->side_stream));
+    PB_CUDA(cudaEventRecord(c->ev_zero, c->side_stream));
+    c->zero_pending = true;
+    return 0;
+  }
+  PB_CUDA(cudaMemsetAsync(c->d_grads, 0, sizeof(float) * c->P, c->stream));
+  return 0;
+}
+int join_zero_grads(pycnn_b200_ctx* c) {
+  if (!c->zero_pending) return 0;
+  c->zero_pending = false;
+  PB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_zero, 0));
+  return 0;
+}
+
 // The output layer's GEMM can finish the training forward pass itself (softmax, CE, dZ, db_o, tallies, bookkeeping)
 bool softmax_fusable(const pycnn_b200_ctx* c) {
   return c->fuse_softmax && c->math_mode == PYCNN_B200_MATH_TF32 && c->C <= 32;
@@ -200,6 +223,7 @@ int forward_logits(pycnn_b200_ctx* c, const float* x, int bs, const int32_t* tra
     g.M = bs; g.N = (int)c->dims[l + 1]; g.K = (int)c->dims[l];
     g.bias = c->d_params + Bt(c, l).off;
     g.cls = (l == 0) ? KC_GEMM_FWD1 : KC_GEMM_FWD;
+    if (l == c->L) PB_TRY(join_zero_grads(c));   // first writer of the gradient buffer (db_o) comes next
     if (l < c->L) { g.C = c->d_act[l]; g.epi = 2; }
     else          { g.C = c->d_probs;  g.epi = 1; }
     g.ldc = c->ldw[l + 1];
@@ -285,14 +309,6 @@ int softmax_ce(pycnn_b200_ctx* c, int bs, const int32_t* labels, bool write_prob
   return 0;
 }
 
-// Gradient buffers are zeroed once per step (zero_grads): split-K dW partial sums and the fused bias-gradient
-// column sums (softmax kernel for the output layer, dA-GEMM epilogue for hidden layers) accumulate into them.
-int zero_grads(pycnn_b200_ctx* c) {
-  LaunchScope ls(c, KC_MISC);
-  PB_CUDA(cudaMemsetAsync(c->d_grads, 0, sizeof(float) * c->P, c->stream));
-  return 0;
-}
-
 // The critical path of the backward pass is dZ_L -> dA chain -> dZ_1 -> dW_1; the shallow dW_l (l >= 1) only need
 // dZ_l and the stored activations, so they are forked onto a side stream as soon as their dZ exists and joined
 // before the gradient exchange / update.  (While per-kernel timing is on everything stays on one stream.)
@@ -364,6 +380,14 @@ int apply_update(pycnn_b200_ctx* c) {
   u.inv_bc1 = (float)(1.0 / bc1); u.inv_bc2 = (float)(1.0 / bc2);
   u.beta1_d = c->beta1; u.beta2_d = c->beta2;
   u.steps_done = c->d_cursor;   // CuPy rule: bias corrections from the device-side step count (graph-replayable)
+  // small networks: norm + clip + update in one launch with a grid barrier (all chunk blocks co-resident:
+  // <= 4 blocks per SM asked of a kernel that fits 8)
+  if (c->update_rule == PYCNN_B200_RULE_CPU && c->fuse_update && c->num_chunks <= c->update_blocks_per_sm * c->num_sms) {
+    LaunchScope ls(c, KC_UPDATE);
+    PB_CUDA(launch_pdl(c, norm_clip_update_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, c->d_params,
+                       (const float*)c->d_grads, c->d_m, c->d_v, (const Chunk*)c->d_chunks, c->d_norm2, u, c->d_update_bar));
+    return 0;
+  }
   if (c->update_rule == PYCNN_B200_RULE_CPU) {   // d_norm2 was zeroed by this step's softmax kernel
     LaunchScope ls(c, KC_SQNORM);
     PB_CUDA(launch_pdl(c, grad_sqnorm_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, (const float*)c->d_grads,
@@ -457,7 +481,7 @@ int join_prefetch(pycnn_b200_ctx* c) {
 // full step on x [bs, Dp] + labels (device).  bs may be 0 on a rank whose slice is empty.
 int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int bs, bool update, int64_t advance = 0) {
   if (bs > 0) {
-    PB_TRY(zero_grads(c));
+    PB_TRY(zero_grads(c, true));
     if (tail_supported(c)) {
       // layer 1 as a raw (bias-free) GEMM, everything after it in one fused kernel
       GemmCall g{};
@@ -467,6 +491,7 @@ int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int 
       g.M = bs; g.N = (int)c->dims[1]; g.K = (int)c->dims[0]; g.epi = 0; g.cls = KC_GEMM_FWD1;
       PB_TRY(gemm(c, g));
       PB_TRY(issue_prefetch(c));
+      PB_TRY(join_zero_grads(c));
       PB_TRY(tail_forward_train(c, bs, labels, advance));
     } else {
       if (softmax_fusable(c)) {
@@ -573,13 +598,19 @@ int prime_rows(pycnn_b200_ctx* c, int bs) {   // first batch of a run -> buffer 
   return gather_batch(c, c->d_idx, c->d_cursor, 0, bs, batch_x(c, 0), batch_labels(c, 0));
 }
 
-int graphed_step_rows_pf(pycnn_b200_ctx* c, int bs, int next_bs, int parity) {
-  return run_graphed(c, std::make_tuple((int)GK_STEP_ROWS_PF, (int64_t)bs, (int64_t)next_bs, (int64_t)bs, parity), [&]() -> int {
-    c->pf.armed = true; c->pf.forked = false; c->pf.next_bs = next_bs; c->pf.extra = bs;
-    c->pf.x = batch_x(c, parity ^ 1); c->pf.labels = batch_labels(c, parity ^ 1);
-    int rc = step_on_batch(c, batch_x(c, parity), batch_labels(c, parity), bs, true, 0);
-    const int rj = join_prefetch(c);
-    return rc ? rc : rj;
+// `count` consecutive steps of bs rows in one graph (count even when > 1 so that the buffer parity comes back to where
+// it started): fewer graph launches per epoch, and the PDL chain runs on across the step boundary.
+int graphed_step_rows_pf(pycnn_b200_ctx* c, int bs, int next_bs, int parity, int count = 1) {
+  return run_graphed(c, std::make_tuple((int)GK_STEP_ROWS_PF, (int64_t)bs, (int64_t)next_bs, (int64_t)count, parity), [&]() -> int {
+    for (int j = 0; j < count; ++j) {
+      const int p = parity ^ (j & 1);
+      c->pf.armed = true; c->pf.forked = false; c->pf.next_bs = (j + 1 < count) ? bs : next_bs; c->pf.extra = bs;
+      c->pf.x = batch_x(c, p ^ 1); c->pf.labels = batch_labels(c, p ^ 1);
+      const int rc = step_on_batch(c, batch_x(c, p), batch_labels(c, p), bs, true, 0);
+      const int rj = join_prefetch(c);
+      if (rc || rj) return rc ? rc : rj;
+    }
+    return 0;
   });
 }
 
@@ -718,12 +749,15 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_pf_join, cudaEventDisableTiming));
   for (auto& ev : c->ev_fork) CREATE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_zero, cudaEventDisableTiming));
   for (auto& ev : c->events) CREATE_CUDA(cudaEventCreate(&ev));
   CREATE_CUDA(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming));
   CREATE_CUDA(cudaMalloc(&c->d_stats, 2 * sizeof(double)));
   CREATE_CUDA(cudaMemset(c->d_stats, 0, 2 * sizeof(double)));
   CREATE_CUDA(cudaMallocHost(&c->h_stats, 2 * sizeof(double)));
+  CREATE_CUDA(cudaMalloc(&c->d_update_bar, 2 * sizeof(unsigned long long)));
+  CREATE_CUDA(cudaMemset(c->d_update_bar, 0, 2 * sizeof(unsigned long long)));
   CREATE_CUDA(cudaMalloc(&c->d_cursor, 2 * sizeof(int64_t)));
   CREATE_CUDA(cudaMemset(c->d_cursor, 0, 2 * sizeof(int64_t)));
 #undef CREATE_CUDA
@@ -731,8 +765,14 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_PDL"); if (g && g[0] == '0') c->use_pdl = false; }
   { const char* g = getenv("PYCNN_B200_FORK"); if (g && g[0] == '0') { cudaStreamDestroy(c->side_stream); c->side_stream = nullptr; } }
   { const char* g = getenv("PYCNN_B200_CARVEOUT"); if (g && g[0] == '0') c->uniform_carveout = false; }
+  { const char* g = getenv("PYCNN_B200_GRAPH_STEPS"); if (g && atoi(g) > 0) c->graph_steps = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PF_CTAS"); if (g && atoi(g) > 0) c->pf_ctas_per_sm = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PREFETCH"); if (g && g[0] == '0') c->use_prefetch = false; }
+  { const char* g = getenv("PYCNN_B200_FUSE_UPDATE"); if (g) c->fuse_update = (g[0] == '1'); }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->update_blocks_per_sm, norm_clip_update_kernel, 256, 0) != cudaSuccess) {
+    c->update_blocks_per_sm = 0; (void)cudaGetLastError();
+  }
+  c->update_blocks_per_sm = std::min(c->update_blocks_per_sm, 4);   // leave room for whatever else is resident
   { const char* g = getenv("PYCNN_B200_FUSE_SOFTMAX"); if (g && g[0] == '0') c->fuse_softmax = false; }
   { const char* g = getenv("PYCNN_B200_ONE_WAVE"); if (g && g[0] == '0') c->one_wave_tiles = false; }
   { const char* g = getenv("PYCNN_B200_PAIR"); if (g && g[0] == '0') c->use_pair = false; }
@@ -749,7 +789,7 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     };
     prefer((const void*)gather_rows_kernel); prefer((const void*)softmax_ce_kernel); prefer((const void*)grad_sqnorm_kernel);
-    prefer((const void*)clip_update_kernel); prefer((const void*)gemm_fixup_kernel); prefer((const void*)step_bookkeeping_kernel);
+    prefer((const void*)clip_update_kernel); prefer((const void*)norm_clip_update_kernel); prefer((const void*)gemm_fixup_kernel); prefer((const void*)step_bookkeeping_kernel);
     prefer((const void*)colsum_kernel); prefer((const void*)p2p::p2p_reduce_kernel); prefer((const void*)p2p::p2p_update_kernel);
     if (e != cudaSuccess) { fail("cudaFuncSetAttribute(carve-out) failed: %s", cudaGetErrorString(e)); return bail(1); }
   }
@@ -766,6 +806,7 @@ int pycnn_b200_destroy(pycnn_b200_ctx* c) {
   drop_graphs(c);
   pycnn_b200_comm_destroy(c);
   free_dev(c->d_cursor);
+  free_dev(c->d_update_bar);
   free_network(c);
   free_dataset(c);
   free_dev(c->d_taps); free_dev(c->d_tc_filters); free_dev(c->d_tc_scale);
@@ -793,6 +834,7 @@ int pycnn_b200_destroy(pycnn_b200_ctx* c) {
   if (c->ev_pf_join) cudaEventDestroy(c->ev_pf_join);
   for (auto& ev : c->ev_fork) if (ev) cudaEventDestroy(ev);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_zero) cudaEventDestroy(c->ev_zero);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -1176,7 +1218,13 @@ int pycnn_b200_train_steps(pycnn_b200_ctx* c, const int64_t* idx, int bs, int st
   if (c->use_prefetch && steps > 1) {
     PB_TRY(ensure_prefetch_buffers(c));
     PB_TRY(prime_rows(c, bs));
-    for (int s = 0; s < steps; ++s) PB_TRY(graphed_step_rows_pf(c, bs, s + 1 < steps ? bs : 0, s & 1));
+    for (int s = 0; s < steps;) {   // greedy 16/8/4/2/1-step graphs, as in train_epoch
+      int count = 1;
+      if ((s & 1) == 0)
+        while (2 * count <= c->graph_steps && s + 2 * count <= steps) count *= 2;
+      PB_TRY(graphed_step_rows_pf(c, bs, s + count < steps ? bs : 0, s & 1, count));
+      s += count;
+    }
   } else {
     for (int s = 0; s < steps; ++s) PB_TRY(graphed_step_rows(c, bs, 0, bs));
   }
@@ -1225,12 +1273,27 @@ int pycnn_b200_train_epoch(pycnn_b200_ctx* c, const int64_t* perm, int64_t n, in
     PB_TRY(prime_rows(c, local_bs(0)));
   }
   int parity = 0;
-  for (int64_t start = 0; start < n; start += batch_size, parity ^= 1) {
+  for (int64_t start = 0; start < n;) {
     const int bs = local_bs(start);
-    // one graph per distinct local batch size (x next size x buffer parity when the row gather is pipelined)
-    if (pipelined) PB_TRY(graphed_step_rows_pf(c, bs, local_bs(start + batch_size), parity));
+    // one graph per distinct local batch size (x next size x buffer parity when the row gather is pipelined);
+    // runs of full batches go graph_steps at a time
+    int count = 1;
+    if (pipelined && parity == 0 && bs > 0) {
+      // largest power-of-two run (<= graph_steps) of full batches that starts here: an epoch decomposes greedily
+      // into 16, 8, 4, 2, 1-step graphs, so only a handful of graphs are ever instantiated
+      for (int U = 1; 2 * U <= c->graph_steps; ) {
+        U *= 2;
+        bool uniform = start + (int64_t)U * batch_size <= n;
+        for (int j = count; uniform && j < U; ++j) uniform = local_bs(start + j * (int64_t)batch_size) == bs;
+        if (!uniform) break;
+        count = U;
+      }
+    }
+    if (pipelined) PB_TRY(graphed_step_rows_pf(c, bs, local_bs(start + count * (int64_t)batch_size), parity, count));
     else           PB_TRY(graphed_step_rows(c, bs, 0, bs));
-    if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += 1;
+    if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += count;
+    start += count * (int64_t)batch_size;
+    if (count & 1) parity ^= 1;
   }
   PB_TRY(read_stats(c, loss_sum, correct, true));
   return 0;

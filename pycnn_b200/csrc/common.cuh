@@ -108,7 +108,8 @@ struct pycnn_b200_ctx {
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // H2D staging for streamed batches
   cudaStream_t side_stream = nullptr;  // backward: the shallow dW GEMMs run beside the dA chain (fork/join inside the graph)
-  cudaEvent_t ev_fork[8] = {}, ev_join = nullptr;
+  cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_zero = nullptr;
+  bool zero_pending = false;           // this step's gradient memset is in flight on side_stream (join_zero_grads)
   cudaStream_t pf_stream = nullptr;    // gather of the NEXT step's rows, overlapped with this step's backward pass
   cudaEvent_t ev_pf_fork = nullptr, ev_pf_join = nullptr;
   struct Prefetch {                    // armed by graphed_step_rows_pf, consumed by step_on_batch
@@ -119,8 +120,12 @@ struct pycnn_b200_ctx {
     int32_t* labels = nullptr;
   } pf;
   bool use_prefetch = true;
+  int graph_steps = 16;                // max training steps per captured graph: a graph launch costs ~15 us of idle GPU (PYCNN_B200_GRAPH_STEPS)
   int pf_ctas_per_sm = 2;              // gather CTAs per SM on the prefetch stream (PYCNN_B200_PF_CTAS)
   bool uniform_carveout = true;        // elementwise kernels ask for the GEMMs' L1/shared split (PYCNN_B200_CARVEOUT=0 disables)
+  bool fuse_update = false;            // norm + clip + update in one launch with a grid barrier (PYCNN_B200_FUSE_UPDATE=1; measured: no gain over two PDL-chained launches)
+  unsigned long long* d_update_bar = nullptr;
+  int update_blocks_per_sm = 0;        // co-resident blocks of norm_clip_update_kernel (grid-barrier safety bound)
   bool fuse_softmax = true;            // training: softmax/CE/dZ in the output-layer GEMM's epilogue (PYCNN_B200_FUSE_SOFTMAX=0: own kernel)
   bool one_wave_tiles = true;          // shallow-K GEMMs: widen the tile rather than run a second wave (PYCNN_B200_ONE_WAVE=0 disables)
   bool use_pair = true;                // M-adjacent GEMM CTAs share the B tile by TMA multicast (PYCNN_B200_PAIR=0 disables)

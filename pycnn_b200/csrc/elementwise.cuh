@@ -71,7 +71,41 @@ __device__ __forceinline__ void gather_rows_body(const float* __restrict__ feat,
   }
 }
 
-__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ feat,
+// Rows of at most 5 x 256 float4 (D <= 5120): a CTA moves two whole rows per iteration -- one index load and one
+// base pointer per row, up to 10 independent 128-bit loads in flight per thread with little address state, so the
+// kernel keeps HBM busy even at the 2 CTAs per SM it gets on the prefetch stream.
+__device__ __forceinline__ void gather_rows_short(const float* __restrict__ feat, const int32_t* __restrict__ labels,
+                                                  const int64_t* __restrict__ idx, int bs, int vec_per_row, int64_t Dp,
+                                                  float* __restrict__ x, int32_t* __restrict__ blabels) {
+  constexpr int NV = 5, RPI = 2;
+  for (int row = blockIdx.x * RPI; row < bs; row += gridDim.x * RPI) {
+    float4 v[RPI][NV];
+    int64_t src[RPI];
+#pragma unroll
+    for (int r = 0; r < RPI; ++r) {
+      src[r] = (row + r < bs) ? idx[row + r] : -1;
+      const float4* s4 = reinterpret_cast<const float4*>(feat + (src[r] < 0 ? 0 : src[r]) * Dp);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = threadIdx.x + j * 256;
+        if (src[r] >= 0 && c < vec_per_row) v[r][j] = ld_stream(s4 + c);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RPI; ++r) {
+      if (src[r] < 0) continue;
+      float4* d4 = reinterpret_cast<float4*>(x + (int64_t)(row + r) * Dp);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = threadIdx.x + j * 256;
+        if (c < vec_per_row) st_stream(d4 + c, v[r][j]);
+      }
+      if (threadIdx.x == 0) blabels[row + r] = labels[src[r]];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 4) gather_rows_kernel(const float* __restrict__ feat,
                                                           const int32_t* __restrict__ labels,
                                                           const int64_t* __restrict__ idx_base,
                                                           const int64_t* __restrict__ cursor, int64_t extra, int bs,
@@ -82,7 +116,9 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
   const int64_t* __restrict__ idx = idx_base + (cursor ? cursor[0] : 0) + extra;
   const int64_t vec_per_row = Dp >> 2;
   const int64_t total = (int64_t)bs * vec_per_row;
-  if (total < (int64_t)0x7fffffff - (int64_t)4 * gridDim.x * blockDim.x)
+  if (vec_per_row <= 5 * 256 && vec_per_row > 2 * 256)
+    gather_rows_short(feat, labels, idx, bs, (int)vec_per_row, Dp, x, blabels);
+  else if (total < (int64_t)0x7fffffff - (int64_t)4 * gridDim.x * blockDim.x)
     gather_rows_body<uint32_t>(feat, labels, idx, (uint32_t)total, (uint32_t)vec_per_row, Dp, x, blabels);
   else
     gather_rows_body<int64_t>(feat, labels, idx, total, vec_per_row, Dp, x, blabels);
@@ -345,6 +381,88 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ pa
     p4[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
     m4[i] = make_float4(me[0], me[1], me[2], me[3]);
     v4[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
+  }
+}
+
+// K7 + update in one launch (CPU rule, networks whose chunks are all co-resident: host checks): every block keeps
+// its chunk's gradient in registers, adds its sum of squares to the tensor's norm, meets the other blocks at a
+// grid barrier, then clips and updates from the registers -- one launch and one read of the gradient less.
+// bar[0] counts block arrivals since the context was created (64-bit, never reset), bar[1] the launches.
+__global__ void __launch_bounds__(256, 4) norm_clip_update_kernel(float* __restrict__ params,
+                                                               const float* __restrict__ grads,
+                                                               float* __restrict__ m, float* __restrict__ v,
+                                                               const Chunk* __restrict__ chunks,
+                                                               double* __restrict__ norm2, UpdateParams u,
+                                                               unsigned long long* __restrict__ bar) {
+  pdl_wait();
+  const Chunk ch = chunks[blockIdx.x];
+  const int64_t n4 = ch.len >> 2;            // <= 512: two 128-bit elements per thread
+  const float4* g4 = reinterpret_cast<const float4*>(grads + ch.off);
+  float4 g[2];
+  float acc = 0.f;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int64_t i = threadIdx.x + e * 256;
+    g[e] = (i < n4) ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    acc = fmaf(g[e].x, g[e].x, acc); acc = fmaf(g[e].y, g[e].y, acc);
+    acc = fmaf(g[e].z, g[e].z, acc); acc = fmaf(g[e].w, g[e].w, acc);
+  }
+  __shared__ double s[8];
+  const double d = warp_sum_d((double)acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += s[i];
+    atomicAdd(&norm2[ch.tensor], t);
+    // grid barrier: every block read bar[1] before it arrives, block 0 bumps it once all have arrived
+    const unsigned long long launch = *reinterpret_cast<volatile unsigned long long*>(bar + 1);
+    const unsigned long long target = (launch + 1ull) * gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1ull);
+    unsigned int polls = 0;
+    while (*reinterpret_cast<volatile unsigned long long*>(bar) < target) {
+      if (++polls > 64u) __nanosleep(32);
+      if (polls > (1u << 24)) __trap();   // blocks not co-resident: protocol bug, do not hang
+    }
+    __threadfence();
+    if (blockIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(bar + 1) = launch + 1ull;
+  }
+  __syncthreads();
+  pdl_launch_dependents();                   // only now: a dependent kernel's CTAs must never take slots this grid still needs
+  const double n2 = __ldcg(&norm2[ch.tensor]);
+  if (!isfinite(n2)) return;                 // NaN/Inf gradient: skip this tensor's update (gradient_decent.pyx:37-39)
+  const double nrm = sqrt(n2);
+  const float scale = (nrm > (double)u.max_norm) ? (float)((double)u.max_norm / nrm) : 1.0f;
+  float4* p4 = reinterpret_cast<float4*>(params + ch.off);
+  float4* m4 = reinterpret_cast<float4*>(m + ch.off);
+  float4* v4 = reinterpret_cast<float4*>(v + ch.off);
+  const float omb1 = 1.0f - u.beta1, omb2 = 1.0f - u.beta2;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int64_t i = threadIdx.x + e * 256;
+    if (i >= n4) continue;
+    const float4 p = p4[i];
+    float pe[4] = {p.x, p.y, p.z, p.w};
+    const float ge[4] = {g[e].x * scale, g[e].y * scale, g[e].z * scale, g[e].w * scale};
+    if (u.opt == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pe[k] -= u.lr * ge[k];
+    } else {
+      const float4 mm = m4[i], vv = v4[i];
+      float me[4] = {mm.x, mm.y, mm.z, mm.w}, ve[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        me[k] = me[k] * u.beta1 + omb1 * ge[k];
+        ve[k] = ve[k] * u.beta2 + omb2 * (ge[k] * ge[k]);
+        const float mh = me[k] * u.inv_bc1;
+        const float vh = fmaxf(ve[k] * u.inv_bc2, u.eps2);
+        pe[k] -= u.lr * mh / (sqrtf(vh) + u.eps);
+      }
+      m4[i] = make_float4(me[0], me[1], me[2], me[3]);
+      v4[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
+    }
+    p4[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
   }
 }
 

@@ -7,12 +7,12 @@ $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "launch list rc=$?"
 $CMD > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 26 -c 13 -o gpurun_out/prof_gemm -f $CMD > gpurun_out/ncu_gemm.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 33 -c 11 -o gpurun_out/prof_gemm -f $CMD > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm profile rc=$?"
 $CMD > gpurun_out/plain3.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:extract_tc -s 2 -c 2 -o gpurun_out/prof_extract -f $CMD > gpurun_out/ncu_extract.log 2>&1
 echo "extract profile rc=$?"
 $CMD > gpurun_out/plain4.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k "regex:gather_rows|clip_update|softmax_ce|grad_sqnorm|gemm_fixup" -s 10 -c 5 -o gpurun_out/prof_elem -f $CMD > gpurun_out/ncu_elem.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:gather_rows|clip_update|grad_sqnorm" -s 9 -c 4 -o gpurun_out/prof_elem -f $CMD > gpurun_out/ncu_elem.log 2>&1
 echo "elementwise profile rc=$?"
 ls -la gpurun_out | head -40

@@ -18,7 +18,10 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_op_gmma.sum",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "lts__t_bytes.sum",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct"]
+
+TRAFFIC = {}   # "<kernel> <grid>" -> DRAM bytes (read + write) of one launch; bench.py reports it as roofline.traffic
 
 
 def short(name):
@@ -70,6 +73,13 @@ def report(rep, name):
         f.write("kernel,grid," + ",".join(f"{k} [{units[i]}]" for k, i in ix.items()) + "\n")
         for r in rows[2:]:
             f.write(f"\"{short(r[h.index('Kernel Name')])}\",\"{r[h.index('Grid Size')]}\"," + ",".join(r[i] for i in ix.values()) + "\n")
+            try:
+                scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                rd, wr = ix["dram__bytes_read.sum"], ix["dram__bytes_write.sum"]
+                b = float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]]
+                TRAFFIC[f"{short(r[h.index('Kernel Name')])} {r[h.index('Grid Size')]}"] = round(b)
+            except (KeyError, ValueError):
+                pass
     print(open(os.path.join(out_dir, f"{tag}_{name}_ncu_full.csv")).read()[:3000])
 
 
@@ -77,3 +87,8 @@ launches()
 report("prof_gemm.ncu-rep", "gemm")
 report("prof_extract.ncu-rep", "extract")
 report("prof_elem.ncu-rep", "elementwise")
+if TRAFFIC:
+    import json
+    with open(os.path.join(out_dir, f"{tag}_traffic.json"), "w") as f:
+        json.dump({"source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures of bench.py (cold L2)",
+                   "bytes_per_launch": TRAFFIC}, f, indent=1, sort_keys=True)
