@@ -587,3 +587,59 @@ def test_error_reporting(lib, ctx):
         ctx.train_step(np.array([0, 99]))
     with pytest.raises(lib.BackendError):
         lib.Context(99)
+
+
+def _epoch_run(lib, env, monkeypatch, mode, opt, n=2100, bs=128, epochs=2, S=32, C=10, layers=(64, 32)):
+    """`epochs` epochs over n rows (short last batch) in a fresh context created under `env`; returns per-epoch
+    (loss, correct) and the final parameters."""
+    for k in ("PYCNN_B200_PREFETCH", "PYCNN_B200_GRAPH_STEPS", "PYCNN_B200_FUSE_SOFTMAX", "PYCNN_B200_CLUSTER_SPLITK",
+              "PYCNN_B200_FORK", "PYCNN_B200_FUSE_UPDATE", "PYCNN_B200_GRAPHS", "PYCNN_B200_CARVEOUT"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    c = lib.Context(0)
+    c.set_math_mode(lib.MATH_FP32_SIMT if mode == "fp32" else lib.MATH_TF32)
+    c.set_filters(O.DEFAULT_FILTERS)
+    D = c.feature_count(S)
+    c.set_network(D, list(layers), C)
+    w, b = O.init_layers(D, list(layers), C, seed=42)
+    wk, bk = O.layer_keys(len(layers))
+    for l, (wn, bn) in enumerate(zip(wk, bk)):
+        c.set_param(2 * l, w[wn])
+        c.set_param(2 * l + 1, b[bn])
+    c.set_optimizer(lib.OPT_ADAM if opt == "adam" else lib.OPT_SGD, 1e-4 if opt == "adam" else 1e-3)
+    c.dataset_alloc(n)
+    c.dataset_extract(0, synth_images(n, S, 77))
+    c.dataset_set_labels(0, synth_labels(n, C, 78))
+    rng = np.random.default_rng(5)
+    stats = [c.train_epoch(rng.permutation(n), bs) for _ in range(epochs)]
+    params = [c.get_param(i) for i in range(c.num_params())]
+    c.close()
+    return stats, params
+
+
+@pytest.mark.parametrize("env", [{"PYCNN_B200_GRAPH_STEPS": "1"}, {"PYCNN_B200_GRAPH_STEPS": "4"}, {"PYCNN_B200_FORK": "0"},
+                                 {"PYCNN_B200_GRAPHS": "0"}, {"PYCNN_B200_FUSE_UPDATE": "1"}, {}],
+                         ids=["graph1", "graph4", "nofork", "eager", "fused_update", "default"])
+def test_step_scheduling_does_not_change_results(lib, monkeypatch, env):
+    """Row-gather prefetch, multi-step graphs, fork/join and the fused norm+update only reschedule the step: two
+    FP32 SGD epochs (17 batches each, short last one) give the plain one-stream path's losses and parameters."""
+    base_stats, base_params = _epoch_run(lib, {"PYCNN_B200_PREFETCH": "0", "PYCNN_B200_FORK": "0"}, monkeypatch, "fp32", "sgd")
+    stats, params = _epoch_run(lib, env, monkeypatch, "fp32", "sgd")
+    for (l0, c0), (l1, c1) in zip(base_stats, stats):
+        assert abs(l0 - l1) <= 1e-6 * abs(l0) and c0 == c1
+    for a, bb in zip(base_params, params):
+        assert rel_err(bb, a) < 1e-5          # float atomics in the bias-gradient column sums: order-dependent last bits
+
+
+@pytest.mark.parametrize("env", [{"PYCNN_B200_FUSE_SOFTMAX": "0"}, {"PYCNN_B200_CLUSTER_SPLITK": "0"}],
+                         ids=["softmax_kernel", "atomic_splitk"])
+def test_fused_epilogues_match_separate_kernels(lib, monkeypatch, env):
+    """TF32 path: softmax/CE in the output-layer GEMM epilogue vs softmax_ce_kernel, cluster (DSMEM) split-K vs global
+    atomics + fix-up pass -- same losses and parameters up to TF32 / summation-order noise."""
+    base_stats, base_params = _epoch_run(lib, {}, monkeypatch, "tf32", "sgd", layers=(256, 64))
+    stats, params = _epoch_run(lib, env, monkeypatch, "tf32", "sgd", layers=(256, 64))
+    for (l0, c0), (l1, c1) in zip(base_stats, stats):
+        assert abs(l0 - l1) <= 2e-3 * abs(l0) and abs(c0 - c1) <= 16
+    for a, bb in zip(base_params, params):
+        assert rel_err(bb, a) < 2e-2
