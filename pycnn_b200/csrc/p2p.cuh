@@ -132,18 +132,24 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chun
       atomicAdd(&norm_part[ch.tensor], tot);
     }
   }
-  // the last block to finish publishes this rank's per-tensor partial norms to every rank
-  __threadfence();
+  // the last block to finish publishes this rank's per-tensor partial norms to every rank.  One fence per block,
+  // after the block barrier: fences are cumulative, so it also orders the other threads' stores (a fence in every
+  // thread costs a MEMBAR per warp and showed up as microseconds).
   __syncthreads();
   __shared__ bool last;
-  if (threadIdx.x == 0) last = (atomicAdd(blocks_done, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicAdd(blocks_done, 1u) == gridDim.x - 1);
+    __threadfence();
+  }
   __syncthreads();
   if (last) {
     for (int i = threadIdx.x; i < t.world * ntensors; i += blockDim.x) {
       const int r = i / ntensors, k = i - r * ntensors;
       t.sync[r]->norms[t.rank][k] = __ldcg(&norm_part[k]);
     }
-    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();
     __syncthreads();
     if (threadIdx.x < t.world) st_release_sys(&t.sync[threadIdx.x]->norms_ready[t.rank], seq);
     for (int k = threadIdx.x; k < ntensors; k += blockDim.x) norm_part[k] = 0.0;   // ready for the next step
@@ -219,10 +225,14 @@ __global__ void __launch_bounds__(256) p2p_update_kernel(PeerTable t, const Chun
     }
   }
   // completion: the last block of this rank publishes "my parameter writes are done" and waits for all peers
-  __threadfence_system();
+  // (one cumulative system-scope fence per block, behind the block barrier, instead of one per thread)
   __syncthreads();
   __shared__ bool last;
-  if (threadIdx.x == 0) last = (atomicAdd(blocks_done, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = (atomicAdd(blocks_done, 1u) == gridDim.x - 1);
+    __threadfence();
+  }
   __syncthreads();
   if (last) {
     if (threadIdx.x == 0) *blocks_done = 0u;
