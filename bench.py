@@ -226,17 +226,30 @@ def run_ours(args):
                    "extract_conv_relu_pool": BS * EXTRACT_BYTES_PER_IMG}
     tf32_peak = pk["bf16_tflops_sustained"] / 2.0
 
+    # DRAM bytes per launch from the committed ncu --set full captures of this same command (profiles/, cold L2)
+    ncu_names = {"gemm_forward_layer1": "gemm_tf32_kernel<256, 0, 0> (1, 32, 4)", "gemm_dW_layer1": "gemm_tf32_kernel<256, 1, 1> (17, 2, 4)",
+                 "gather_rows": "gather_rows_kernel (296, 1, 1)", "clip_update": "clip_update_kernel (560, 1, 1)",
+                 "grad_sqnorm": "grad_sqnorm_kernel (560, 1, 1)"}
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
+            ncu_traffic = json.load(f)["bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        ncu_traffic = {}
+
+    def traffic_of(k):
+        return ncu_traffic.get(ncu_names.get(k, ""))
+
     def roofline_of(k):
         """algorithmic FLOPs (or bytes) of one launch / average CUDA-event duration of one launch of class k"""
         ms_launch = per_class[k]["ms_per_step"] / per_class[k]["launches_per_step"]
         if k in class_flops:
             ach = class_flops[k] / per_class[k]["ms_per_step"] / 1e9          # whole class per step (TFLOP/s)
             return {"kernel": k, "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-                    "frac": ach / tf32_peak, "traffic": None, "us_per_launch": ms_launch * 1e3,
+                    "frac": ach / tf32_peak, "traffic": traffic_of(k), "us_per_launch": ms_launch * 1e3,
                     "peak_source": f"{pk['source']} bf16 sustained / 2 (tf32 runs at half the bf16 rate)"}
         ach = class_bytes.get(k, 0) / per_class[k]["ms_per_step"] / 1e6          # GB/s
         return {"kernel": k, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": None, "us_per_launch": ms_launch * 1e3, "peak_source": pk["source"]}
+                "frac": ach / pk["hbm_gbs"], "traffic": traffic_of(k), "us_per_launch": ms_launch * 1e3, "peak_source": pk["source"]}
 
     # dominant kernel: the single-kernel class with the largest share of the step (the "tail" classes are groups of
     # several tiny latency-bound GEMMs and are reported in rooflines_all); a split-K GEMM's zero-fill and fix-up
