@@ -106,6 +106,9 @@ int pycnn_b200_set_opt_state(pycnn_b200_ctx* ctx, int which, int index, const do
 int pycnn_b200_set_optimizer(pycnn_b200_ctx* ctx, int kind, double lr, double beta1, double beta2,
                              double eps);
 int pycnn_b200_get_step_count(pycnn_b200_ctx* ctx, int64_t* t);
+/* resume: restore the Adam step count t of the CuPy update rule (pycnn/pycnn.py:534) after set_optimizer +
+ * set_opt_state; the CPU rule never advances t (pycnn/modules/gradient_decent.pyx:58-59) and ignores it */
+int pycnn_b200_set_step_count(pycnn_b200_ctx* ctx, int64_t t);
 
 /* ---- device-resident dataset (replaces self.data/self.labels migration, pycnn.py:192-194) -- */
 int pycnn_b200_dataset_alloc(pycnn_b200_ctx* ctx, int64_t capacity_rows);

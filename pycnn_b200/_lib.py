@@ -59,6 +59,7 @@ _SIGNATURES = {
     "pycnn_b200_set_opt_state": [c_ctx, I, I, _dp],
     "pycnn_b200_set_optimizer": [c_ctx, I, D, D, D, D],
     "pycnn_b200_get_step_count": [c_ctx, _i64p],
+    "pycnn_b200_set_step_count": [c_ctx, ctypes.c_int64],
     "pycnn_b200_dataset_alloc": [c_ctx, I64],
     "pycnn_b200_dataset_extract": [c_ctx, I64, _u8p, I64, I],
     "pycnn_b200_dataset_set_features": [c_ctx, I64, _dp, I64],
@@ -285,6 +286,9 @@ class Context:
         t = ctypes.c_int64()
         check(self.lib.pycnn_b200_get_step_count(self.handle, ctypes.byref(t)))
         return t.value
+
+    def set_step_count(self, t: int):
+        check(self.lib.pycnn_b200_set_step_count(self.handle, int(t)))
 
     # -- dataset -----------------------------------------------------------------------------
     def dataset_alloc(self, rows):

@@ -1103,6 +1103,15 @@ int pycnn_b200_get_step_count(pycnn_b200_ctx* c, int64_t* t) {
   return 0;
 }
 
+int pycnn_b200_set_step_count(pycnn_b200_ctx* c, int64_t t) {
+  CTX_GUARD(c);
+  PB_CHECK(t >= 0, "step count must be >= 0 (got %lld)", (long long)t);
+  PB_CUDA(cudaStreamSynchronize(c->stream));
+  PB_CUDA(cudaMemcpy(c->d_cursor + 1, &t, sizeof(int64_t), cudaMemcpyHostToDevice));
+  c->t = t;
+  return 0;
+}
+
 // ---- dataset -----------------------------------------------------------------------------------
 int pycnn_b200_dataset_alloc(pycnn_b200_ctx* c, int64_t rows) {
   CTX_GUARD(c);

@@ -110,6 +110,7 @@ class PyCNN:
         self._net_key = None            # (D, layers, C) the device network was built for
         self._params_on_device = False
         self._opt_key = None
+        self._resumed = False           # load_checkpoint() restored device state that train_model must keep
         self._rank, self._world = 0, 1
 
     # ------------------------------------------------------------------ backend seam (:104-194)
@@ -450,7 +451,9 @@ class PyCNN:
         self.t = ctx.step_count()
 
     # ------------------------------------------------------------------ training (:572-686)
-    def train_model(self, visualize=False, early_stop=0):
+    def train_model(self, visualize=False, early_stop=0, start_epoch=0, checkpoint=None, checkpoint_every=1):
+        """pycnn/pycnn.py:572-686.  Additive keywords: `start_epoch` resumes the epoch counter after
+        load_checkpoint(); `checkpoint` = path of a resumable sidecar written every `checkpoint_every` epochs."""
         if not hasattr(self, "data") or len(self.data) == 0:
             raise ValueError("No data loaded. Please load a dataset first using dataset.local() or dataset.hf()")
         ctx = self._require()
@@ -458,12 +461,13 @@ class PyCNN:
             print("=" * 50)
             print("Training the model...")
         self.visualize = visualize
-        self._push_params(force=True)
+        self._push_params(force=not self._resumed)
         ctx, num_samples = self._push_dataset()
         self._push_optimizer()
+        self._resumed = False
         plot = _LivePlot(self.epochs) if visualize else None
         best_loss, stop_counter, patience = float("inf"), 0, early_stop
-        for epoch in range(self.epochs):
+        for epoch in range(int(start_epoch), self.epochs):
             perm = np.random.permutation(num_samples)                     # :622, host stream
             loss_sum, correct = ctx.train_epoch(perm, self.batch_size)    # :626-642 in one call
             epoch_loss = loss_sum / max(1, num_samples)
@@ -482,6 +486,8 @@ class PyCNN:
                       f"acc={epoch_acc:.4f}  loss={epoch_loss:.6f}   ", end="")
             if plot:
                 plot.update(epoch, epoch_loss, epoch_acc)
+            if checkpoint and self._rank == 0 and (epoch + 1) % max(1, int(checkpoint_every)) == 0:
+                self.save_checkpoint(checkpoint, epoch=epoch + 1, quiet=True)
             if epoch_loss <= 1e-6 and epoch_acc >= 0.999999 and epoch < self.epochs:
                 if self._rank == 0:
                     print(f"\nModel reached maximum learning on epoch {epoch}")
@@ -528,6 +534,68 @@ class PyCNN:
         print(f"Network architecture: {len(self.layers)} hidden layers: {self.layers}")
         if trained_with_cuda != self.use_cuda:
             print("Backend conversion completed automatically.")
+
+    # ------------------------------------------------------------------ resumable checkpoints
+    CHECKPOINT_FORMAT = "pycnn_b200.checkpoint/1"
+
+    def save_checkpoint(self, path="checkpoint.bin", epoch=None, quiet=False):
+        """Additive sidecar to model.bin (whose dict layout is untouched, :688-706): the same model dict plus what
+        the reference cannot restore -- Adam m, v, t, hyper-parameters, the epoch reached and the host NumPy RNG
+        state that drives np.random.permutation (:622) -- so that load_checkpoint() + train_model(start_epoch=...)
+        continues the run it was taken from."""
+        ctx = self._require()
+        if self._params_on_device:
+            self._pull_params()
+        m, v = self.optimizer_state() if self._opt_key is not None else ({}, {})
+        blob = {
+            "format": self.CHECKPOINT_FORMAT,
+            "model": {"weights": {k: np.asarray(x, dtype=np.float64) for k, x in self.weights.items()},
+                      "biases": {k: np.asarray(x, dtype=np.float64) for k, x in self.biases.items()},
+                      "filters": self.filters, "image_size": int(self.image_size), "classes": list(self.classes),
+                      "layers": self.layers, "trained_with_cuda": self.use_cuda},
+            "optimizer": {"kind": self.optimizer, "learning_rate": float(self.learning_rate), "beta1": self.beta1,
+                          "beta2": self.beta2, "eps": self.eps, "m": m, "v": v, "t": int(ctx.step_count())},
+            "epoch": None if epoch is None else int(epoch), "epochs": int(self.epochs), "batch_size": int(self.batch_size),
+            "numpy_rng_state": np.random.get_state(),
+        }
+        tmp = f"{path}.tmp"
+        with open(tmp, "wb") as f:
+            pickle.dump(blob, f, protocol=4)
+        os.replace(tmp, path)                      # a crash mid-write never leaves a truncated checkpoint
+        if not quiet:
+            print(f"Checkpoint saved in {path} with {round(os.path.getsize(path) / (1024 * 1024), 2)}MB")
+
+    def load_checkpoint(self, path="checkpoint.bin", restore_rng=True):
+        """Restore a save_checkpoint() file into this model and its device context; returns the epoch it was taken
+        at (pass it as train_model(start_epoch=...))."""
+        with open(path, "rb") as f:
+            blob = pickle.load(f)
+        if not isinstance(blob, dict) or blob.get("format") != self.CHECKPOINT_FORMAT:
+            raise ValueError(f"{path} is not a {self.CHECKPOINT_FORMAT} file (model.bin files load with load_model)")
+        mdl, opt = blob["model"], blob["optimizer"]
+        self.weights = {k: np.array(x, dtype=np.float64) for k, x in mdl["weights"].items()}
+        self.biases = {k: np.array(x, dtype=np.float64) for k, x in mdl["biases"].items()}
+        self.filters, self.image_size = mdl["filters"], mdl["image_size"]
+        self.classes, self.layers = mdl["classes"], mdl.get("layers", [])
+        self.optimizer, self.learning_rate = opt["kind"], opt["learning_rate"]
+        self.beta1, self.beta2, self.eps = opt["beta1"], opt["beta2"], opt["eps"]
+        self.epochs, self.batch_size = blob.get("epochs", self.epochs), blob.get("batch_size", self.batch_size)
+        self._params_on_device = False
+        ctx = self._push_params(force=True)
+        self._opt_key = None
+        self._push_optimizer()                     # zeroes m, v, t ...
+        wk, bk = self._keys()
+        for l, (w, b) in enumerate(zip(wk, bk)):   # ... then put the saved state back
+            for which, state in ((0, opt["m"]), (1, opt["v"])):
+                if w in state:
+                    ctx.set_opt_state(which, 2 * l, state[w])
+                    ctx.set_opt_state(which, 2 * l + 1, state[b])
+        ctx.set_step_count(int(opt.get("t", 0)))
+        self.t = int(opt.get("t", 0))
+        if restore_rng and blob.get("numpy_rng_state") is not None:
+            np.random.set_state(blob["numpy_rng_state"])
+        self._resumed = True                       # train_model must not overwrite the restored device state
+        return blob.get("epoch")
 
     # ------------------------------------------------------------------ inference (:737-773)
     def predict(self, img_path):

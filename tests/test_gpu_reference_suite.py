@@ -204,3 +204,53 @@ def test_adam_and_private_call_protocol(dataset_dir):
     for k in w:
         assert np.abs(m.weights[k] - w[k]).max() / np.abs(w[k]).max() < 1e-3, k
     assert m.t == 0
+
+
+@pytest.mark.parametrize("rule", ["cpu", "cupy"])
+def test_checkpoint_resume_continues_the_run(tmp_path, rule):
+    """an additive sidecar (model dict + Adam m, v, t + epoch + host RNG state).  2 epochs, checkpoint,
+    fresh model + load_checkpoint + 2 more epochs == 4 epochs straight (Adam, FP32 mode; both update rules: the CuPy
+    rule's bias correction needs the restored step count)."""
+    from pycnn_b200 import PyCNN
+    rng = np.random.default_rng(9)
+    imgs = rng.integers(0, 256, (96, 32, 32, 3), dtype=np.uint8)
+    lab = rng.integers(0, 3, 96)
+    ckpt = str(tmp_path / "run.ckpt")
+
+    def fresh(epochs):
+        m = PyCNN()
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.init(batch_size=32, layers=[24, 12], learning_rate=1e-3, epochs=epochs)
+            m.adam()
+            m.set_math_mode("fp32")
+            m.set_update_rule(rule)
+            m.cuda(True)
+            np.random.seed(42)
+            m.dataset.synthetic(imgs, lab, ["a", "b", "c"])
+        return m
+
+    straight = fresh(4)
+    np.random.seed(7)
+    quiet(straight.train_model)
+
+    first = fresh(2)
+    np.random.seed(7)
+    quiet(first.train_model, checkpoint=ckpt)
+    assert os.path.exists(ckpt) and not os.path.exists(ckpt + ".tmp")
+
+    resumed = fresh(4)
+    np.random.seed(999)                                   # the checkpoint, not this, decides the next permutation
+    (epoch, _) = quiet(resumed.load_checkpoint, ckpt)
+    assert epoch == 2 and resumed.optimizer == "adam"
+    resumed.epochs = 4
+    _, out = quiet(resumed.train_model, start_epoch=epoch)
+    assert "epoch=3/4" in out and "epoch=4/4" in out and "epoch=1/4" not in out
+    for k in straight.weights:
+        assert np.abs(resumed.weights[k] - straight.weights[k]).max() <= 2e-6 * np.abs(straight.weights[k]).max(), k
+    for k in straight.biases:
+        assert np.abs(resumed.biases[k] - straight.biases[k]).max() <= 2e-6 * max(np.abs(straight.biases[k]).max(), 1e-3), k
+    # the sidecar does not replace model.bin: load_model refuses nothing it used to accept, load_checkpoint refuses model.bin
+    mb = str(tmp_path / "model.bin")
+    quiet(resumed.save_model, mb)
+    with pytest.raises(ValueError):
+        resumed.load_checkpoint(mb)
