@@ -207,6 +207,12 @@ int pycnn_b200_kernel_stats(pycnn_b200_ctx* ctx, int cls, int64_t* launches, dou
 /* total kernel launches issued by this context since creation */
 int pycnn_b200_launch_count(pycnn_b200_ctx* ctx, int64_t* launches);
 /* write >= L2-size bytes to evict L2 between timed iterations */
+/* In-kernel timeline (diagnostics; no reference counterpart): op 0 = enable with `capacity` slots (drops captured graphs
+ * so that new captures carry slots), 1 = reset all slots, 2 = disable.  Every traced launch (GEMMs, row gather, norm,
+ * update) records {first CTA start, last CTA end} in %globaltimer ns; read returns the slots handed out so far:
+ * times[2*i], times[2*i+1] and kinds[i] = kernel class + 100 * stream (0 main, 1 side, 2 prefetch). */
+int pycnn_b200_trace_control(pycnn_b200_ctx* ctx, int op, int capacity);
+int pycnn_b200_trace_read(pycnn_b200_ctx* ctx, uint64_t* times, int32_t* kinds, int capacity, int* count);
 int pycnn_b200_flush_l2(pycnn_b200_ctx* ctx);
 /* standalone GEMM probe for tests/roofline: C[M,N] = op(A) . op(B) with the context's math mode.
  * a_kmajor: A stored [M,K] row-major (1) or [K,M] row-major (0); b_kmajor: B stored [N,K] (1) or

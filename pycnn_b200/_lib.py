@@ -59,6 +59,8 @@ _SIGNATURES = {
     "pycnn_b200_set_opt_state": [c_ctx, I, I, _dp],
     "pycnn_b200_set_optimizer": [c_ctx, I, D, D, D, D],
     "pycnn_b200_get_step_count": [c_ctx, _i64p],
+    "pycnn_b200_trace_control": [c_ctx, ctypes.c_int, ctypes.c_int],
+    "pycnn_b200_trace_read": [c_ctx, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.POINTER(ctypes.c_int)],
     "pycnn_b200_set_step_count": [c_ctx, ctypes.c_int64],
     "pycnn_b200_dataset_alloc": [c_ctx, I64],
     "pycnn_b200_dataset_extract": [c_ctx, I64, _u8p, I64, I],
@@ -287,6 +289,33 @@ class Context:
         check(self.lib.pycnn_b200_get_step_count(self.handle, ctypes.byref(t)))
         return t.value
 
+    # -- in-kernel timeline (diagnostics) ----------------------------------------------------------
+    def trace_enable(self, capacity=4096):
+        check(self.lib.pycnn_b200_trace_control(self.handle, 0, int(capacity)))
+        self._trace_cap = int(capacity)
+
+    def trace_reset(self):
+        check(self.lib.pycnn_b200_trace_control(self.handle, 1, 0))
+
+    def trace_disable(self):
+        check(self.lib.pycnn_b200_trace_control(self.handle, 2, 0))
+
+    def trace_read(self):
+        """-> list of (kernel class name, stream id, start_ns, end_ns) in launch order; untouched slots are skipped."""
+        cap = self._trace_cap
+        times = np.zeros(2 * cap, np.uint64)
+        kinds = np.zeros(cap, np.int32)
+        n = ctypes.c_int()
+        check(self.lib.pycnn_b200_trace_read(self.handle, ptr(times, ctypes.c_uint64), ptr(kinds, ctypes.c_int32), cap, ctypes.byref(n)))
+        names = self.kernel_class_names()
+        out = []
+        for i in range(n.value):
+            t0, t1 = int(times[2 * i]), int(times[2 * i + 1])
+            if t1 == 0:
+                continue
+            out.append((names[int(kinds[i]) % 100], int(kinds[i]) // 100, t0, t1))
+        return out
+
     def set_step_count(self, t: int):
         check(self.lib.pycnn_b200_set_step_count(self.handle, int(t)))
 
@@ -466,6 +495,9 @@ class Context:
 
     def set_kernel_timing(self, on: bool):
         check(self.lib.pycnn_b200_set_kernel_timing(self.handle, int(bool(on))))
+
+    def kernel_class_names(self):
+        return [self.lib.pycnn_b200_kernel_class_name(k).decode() for k in range(self.lib.pycnn_b200_kernel_class_count())]
 
     def kernel_stats(self, reset=False):
         out = {}

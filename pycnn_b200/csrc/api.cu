@@ -312,8 +312,16 @@ int softmax_ce(pycnn_b200_ctx* c, int bs, const int32_t* labels, bool write_prob
 // The critical path of the backward pass is dZ_L -> dA chain -> dZ_1 -> dW_1; the shallow dW_l (l >= 1) only need
 // dZ_l and the stored activations, so they are forked onto a side stream as soon as their dZ exists and joined
 // before the gradient exchange / update.  (While per-kernel timing is on everything stays on one stream.)
+//
+// The last shallow dW (layer 2) becomes ready only ~10 us before dW_1 and its 32 split-K CTAs used to hold SMs that
+// dW_1's single wave (136 CTAs at configs[1]) then had to wait for (+7 us on the critical path, scripts/
+// step_timeline.py).  It is therefore released together with dW_1 (same dependency: the last dA GEMM) and capped to
+// the SMs dW_1 leaves idle, so that it runs entirely in dW_1's shadow.
 int backward(pycnn_b200_ctx* c, const float* x, int bs) {
   const bool fork = !c->timing && c->side_stream != nullptr && c->L >= 1 && c->L < 8;
+  const bool defer = fork && c->defer_last_dw && c->math_mode == PYCNN_B200_MATH_TF32;
+  GemmCall deferred{};
+  bool have_deferred = false;
   cudaStream_t main_stream = c->stream;
   for (int l = c->L; l >= 0; --l) {
     const float* in = (l == 0) ? x : c->d_act[l - 1];
@@ -325,7 +333,9 @@ int backward(pycnn_b200_ctx* c, const float* x, int bs) {
       g.C = c->d_grads + Wt(c, l).off; g.ldc = Wt(c, l).ld;
       g.M = out_n; g.N = in_n; g.K = bs; g.epi = 0; g.cls = (l == 0) ? KC_GEMM_DW1 : KC_GEMM_DW;
       g.c_is_zero = true;
-      if (fork && l > 0) {
+      if (defer && l == 1) {
+        deferred = g; have_deferred = true;      // launched below, behind dW of layer 1
+      } else if (fork && l > 0) {
         PB_CUDA(cudaEventRecord(c->ev_fork[l], main_stream));
         PB_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork[l], 0));
         c->stream = c->side_stream;
@@ -346,7 +356,17 @@ int backward(pycnn_b200_ctx* c, const float* x, int bs) {
       g.colsum = c->d_grads + Bt(c, l - 1).off;
       g.cls = KC_GEMM_DA;
       PB_TRY(gemm(c, g));
+      if (have_deferred && l == 1) PB_CUDA(cudaEventRecord(c->ev_fork[1], main_stream));   // = dW_1's dependency
     }
+  }
+  if (have_deferred) {
+    const int room = c->num_sms - c->last_gemm_ctas;      // last launch on this path: dW of layer 1
+    if (room >= 8) deferred.max_ctas = room;
+    PB_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork[1], 0));
+    c->stream = c->side_stream;
+    const int rc = gemm(c, deferred);
+    c->stream = main_stream;
+    PB_TRY(rc);
   }
   if (fork) {   // join: everything the side stream did is ordered before the exchange / update
     PB_CUDA(cudaEventRecord(c->ev_join, c->side_stream));
@@ -391,11 +411,12 @@ int apply_update(pycnn_b200_ctx* c) {
   if (c->update_rule == PYCNN_B200_RULE_CPU) {   // d_norm2 was zeroed by this step's softmax kernel
     LaunchScope ls(c, KC_SQNORM);
     PB_CUDA(launch_pdl(c, grad_sqnorm_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, (const float*)c->d_grads,
-                       (const Chunk*)c->d_chunks, c->d_norm2));
+                       (const Chunk*)c->d_chunks, c->d_norm2, trace_slot(c, KC_SQNORM)));
   }
   LaunchScope ls(c, KC_UPDATE);
   PB_CUDA(launch_pdl(c, clip_update_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, c->d_params,
-                     (const float*)c->d_grads, c->d_m, c->d_v, (const Chunk*)c->d_chunks, (const double*)c->d_norm2, u));
+                     (const float*)c->d_grads, c->d_m, c->d_v, (const Chunk*)c->d_chunks, (const double*)c->d_norm2, u,
+                     trace_slot(c, KC_UPDATE)));
   return 0;
 }
 
@@ -535,7 +556,7 @@ int gather_batch(pycnn_b200_ctx* c, const int64_t* d_idx, const int64_t* cursor,
   const int per_sm = (c->stream == c->pf_stream) ? c->pf_ctas_per_sm : 8;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)per_sm * c->num_sms));
   PB_CUDA(launch_pdl(c, gather_rows_kernel, dim3(blocks), dim3(256), 0, c->stream, c->d_feat,
-                     c->d_labels, d_idx, cursor, extra, bs, c->Dp, x, blabels));
+                     c->d_labels, d_idx, cursor, extra, bs, c->Dp, x, blabels, trace_slot(c, KC_GATHER)));
   return 0;
 }
 
@@ -737,12 +758,16 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   c->l2_bytes = (size_t)prop.l2CacheSize;
   auto bail = [&](int r) { pycnn_b200_destroy(c); return r; };
 #define CREATE_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { fail("%s failed: %s", #expr, cudaGetErrorString(_e)); return bail(1); } } while (0)
-  CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  CREATE_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
   {
-    int prio_lo = 0, prio_hi = 0;   // the prefetch gather yields SM slots to the critical path
+    // the critical path (main stream) gets the highest priority: when CTAs of several streams are pending, its
+    // CTAs are placed first; the prefetch gather and the shallow dW GEMMs take what is left
+    int prio_lo = 0, prio_hi = 0;
     CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    const char* pe = getenv("PYCNN_B200_PRIORITIES");
+    const bool prio = !(pe && pe[0] == '0');
+    CREATE_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio ? prio_hi : prio_lo));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_lo));
     CREATE_CUDA(cudaStreamCreateWithPriority(&c->pf_stream, cudaStreamNonBlocking, prio_lo));
   }
   CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_pf_fork, cudaEventDisableTiming));
@@ -765,6 +790,7 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_PDL"); if (g && g[0] == '0') c->use_pdl = false; }
   { const char* g = getenv("PYCNN_B200_FORK"); if (g && g[0] == '0') { cudaStreamDestroy(c->side_stream); c->side_stream = nullptr; } }
   { const char* g = getenv("PYCNN_B200_CARVEOUT"); if (g && g[0] == '0') c->uniform_carveout = false; }
+  { const char* g = getenv("PYCNN_B200_DEFER_DW"); if (g && g[0] == '0') c->defer_last_dw = false; }
   { const char* g = getenv("PYCNN_B200_GRAPH_STEPS"); if (g && atoi(g) > 0) c->graph_steps = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PF_CTAS"); if (g && atoi(g) > 0) c->pf_ctas_per_sm = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PREFETCH"); if (g && g[0] == '0') c->use_prefetch = false; }
@@ -807,6 +833,7 @@ int pycnn_b200_destroy(pycnn_b200_ctx* c) {
   pycnn_b200_comm_destroy(c);
   free_dev(c->d_cursor);
   free_dev(c->d_update_bar);
+  free_dev(c->d_trace);
   free_network(c);
   free_dataset(c);
   free_dev(c->d_taps); free_dev(c->d_tc_filters); free_dev(c->d_tc_scale);
@@ -1777,6 +1804,48 @@ int pycnn_b200_kernel_stats(pycnn_b200_ctx* c, int cls, int64_t* launches, doubl
 int pycnn_b200_launch_count(pycnn_b200_ctx* c, int64_t* launches) {
   PB_CHECK(c && launches, "null argument");
   *launches = c->launches;
+  return 0;
+}
+
+static int trace_fill(pycnn_b200_ctx* c) {
+  std::vector<unsigned long long> init(2 * (size_t)c->trace_cap);
+  for (int i = 0; i < c->trace_cap; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+  PB_CUDA(cudaMemcpy(c->d_trace, init.data(), sizeof(unsigned long long) * init.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int pycnn_b200_trace_control(pycnn_b200_ctx* c, int op, int capacity) {
+  CTX_GUARD(c);
+  PB_CUDA(cudaStreamSynchronize(c->stream));
+  if (op == 0) {
+    PB_CHECK(capacity > 0 && capacity <= (1 << 20), "trace capacity %d out of range", capacity);
+    drop_graphs(c);
+    free_dev(c->d_trace); c->d_trace = nullptr;
+    PB_CUDA(cudaMalloc(&c->d_trace, sizeof(unsigned long long) * 2 * (size_t)capacity));
+    c->trace_cap = capacity; c->trace_next = 0; c->trace_cls.clear(); c->trace = true;
+    return trace_fill(c);
+  }
+  if (op == 1) {
+    PB_CHECK(c->d_trace, "trace is not enabled");
+    return trace_fill(c);
+  }
+  PB_CHECK(op == 2, "unknown trace op %d", op);
+  drop_graphs(c);   // captured launches hold slot pointers
+  c->trace = false;
+  free_dev(c->d_trace); c->d_trace = nullptr;
+  c->trace_cap = c->trace_next = 0; c->trace_cls.clear();
+  return 0;
+}
+
+int pycnn_b200_trace_read(pycnn_b200_ctx* c, uint64_t* times, int32_t* kinds, int capacity, int* count) {
+  CTX_GUARD(c);
+  PB_CHECK(times && kinds && count, "null argument");
+  PB_CHECK(c->d_trace, "trace is not enabled");
+  PB_CUDA(cudaStreamSynchronize(c->stream));
+  const int n = std::min(capacity, c->trace_next);
+  if (n > 0) PB_CUDA(cudaMemcpy(times, c->d_trace, sizeof(unsigned long long) * 2 * (size_t)n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) kinds[i] = c->trace_cls[i];
+  *count = n;
   return 0;
 }
 

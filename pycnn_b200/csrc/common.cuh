@@ -119,6 +119,14 @@ struct pycnn_b200_ctx {
     float* x = nullptr;
     int32_t* labels = nullptr;
   } pf;
+  // in-kernel timeline (PYCNN_B200_TRACE=1, diagnostics): every traced launch owns a slot {first CTA start, last CTA
+  // end} in %globaltimer ns; slots are handed out in launch order while a step is issued or captured
+  bool trace = false;
+  unsigned long long* d_trace = nullptr;
+  int trace_cap = 0, trace_next = 0;
+  std::vector<int> trace_cls;          // kernel class of each slot, + 100 x stream id (0 main, 1 side, 2 prefetch)
+  int last_gemm_ctas = 0;              // grid size of the most recent tensor-core GEMM launch
+  bool defer_last_dw = true;           // backward: dW of layer 2 runs on the SMs dW of layer 1 leaves idle (PYCNN_B200_DEFER_DW=0)
   bool use_prefetch = true;
   int graph_steps = 16;                // max training steps per captured graph: a graph launch costs ~15 us of idle GPU (PYCNN_B200_GRAPH_STEPS)
   int pf_ctas_per_sm = 2;              // gather CTAs per SM on the prefetch stream (PYCNN_B200_PF_CTAS)
@@ -281,6 +289,17 @@ struct LaunchScope {
 // Programmatic dependent launch: the next kernel of the step may start launching (and run its prologue) while
 // this one drains; every kernel calls pdl_wait() before it touches global memory produced by its predecessor.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_begin(unsigned long long* slot) {
+  if (slot && threadIdx.x == 0) atomicMin(slot, global_timer_ns());
+}
+__device__ __forceinline__ void trace_end(unsigned long long* slot) {
+  if (slot && threadIdx.x == 0) atomicMax(slot + 1, global_timer_ns());
+}
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // launch as thread-block clusters of (1, cluster_y, cluster_z) when that is more than one CTA
@@ -313,6 +332,14 @@ template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl(pycnn_b200_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                      cudaStream_t stream, Args&&... args) {
   return launch_pdl_cluster(c, kernel, grid, block, smem, stream, 1, 1, static_cast<Args&&>(args)...);
+}
+
+// next timeline slot for a launch of class `cls` on c->stream (nullptr when tracing is off or the table is full)
+static inline unsigned long long* trace_slot(pycnn_b200_ctx* c, int cls) {
+  if (!c->trace || !c->d_trace || c->trace_next >= c->trace_cap) return nullptr;
+  const int sid = (c->stream == c->side_stream) ? 1 : (c->stream == c->pf_stream) ? 2 : 0;
+  c->trace_cls.push_back(cls + 100 * sid);
+  return c->d_trace + 2 * (size_t)(c->trace_next++);
 }
 
 static inline int ensure_scratch(pycnn_b200_ctx* c, size_t bytes) {

@@ -110,9 +110,11 @@ __global__ void __launch_bounds__(256, 4) gather_rows_kernel(const float* __rest
                                                           const int64_t* __restrict__ idx_base,
                                                           const int64_t* __restrict__ cursor, int64_t extra, int bs,
                                                           int64_t Dp, float* __restrict__ x,
-                                                          int32_t* __restrict__ blabels) {
+                                                          int32_t* __restrict__ blabels,
+                                                          unsigned long long* trace) {
   pdl_wait();
   pdl_launch_dependents();
+  trace_begin(trace);
   const int64_t* __restrict__ idx = idx_base + (cursor ? cursor[0] : 0) + extra;
   const int64_t vec_per_row = Dp >> 2;
   const int64_t total = (int64_t)bs * vec_per_row;
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(256, 4) gather_rows_kernel(const float* __rest
     gather_rows_body<uint32_t>(feat, labels, idx, (uint32_t)total, (uint32_t)vec_per_row, Dp, x, blabels);
   else
     gather_rows_body<int64_t>(feat, labels, idx, total, vec_per_row, Dp, x, blabels);
+  trace_end(trace);
 }
 
 // Zero-copy batch assembly: rows idx[i] of a pinned host array (device-visible through UVA) are pulled over
@@ -288,9 +291,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restrict__ grads,
                                                           const Chunk* __restrict__ chunks,
-                                                          double* __restrict__ norm2) {
+                                                          double* __restrict__ norm2, unsigned long long* trace) {
   pdl_wait();
   pdl_launch_dependents();
+  trace_begin(trace);
   const Chunk ch = chunks[blockIdx.x];
   const float4* g4 = reinterpret_cast<const float4*>(grads + ch.off);
   const int64_t n4 = ch.len >> 2;  // chunk offsets/lengths are multiples of 4
@@ -311,6 +315,7 @@ __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restric
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s[i];
     atomicAdd(&norm2[ch.tensor], t);
   }
+  trace_end(trace);
 }
 
 struct UpdateParams {
@@ -330,9 +335,11 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ pa
                                                           const float* __restrict__ grads,
                                                           float* __restrict__ m, float* __restrict__ v,
                                                           const Chunk* __restrict__ chunks,
-                                                          const double* __restrict__ norm2, UpdateParams u) {
+                                                          const double* __restrict__ norm2, UpdateParams u,
+                                                          unsigned long long* trace) {
   pdl_wait();
   pdl_launch_dependents();
+  trace_begin(trace);
   const Chunk ch = chunks[blockIdx.x];
   float scale = 1.0f;
   if (u.rule == 1 && u.opt == 1) {   // pycnn/pycnn.py:534,544-545: t advances, 1 - beta^t
@@ -359,6 +366,7 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ pa
       p.w -= u.lr * (g.w * scale);
       p4[i] = p;
     }
+    trace_end(trace);
     return;
   }
   float4* m4 = reinterpret_cast<float4*>(m + ch.off);
@@ -382,6 +390,7 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ pa
     m4[i] = make_float4(me[0], me[1], me[2], me[3]);
     v4[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
   }
+  trace_end(trace);
 }
 
 // K7 + update in one launch (CPU rule, networks whose chunks are all co-resident: host checks): every block keeps

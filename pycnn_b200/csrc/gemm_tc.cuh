@@ -63,6 +63,7 @@ struct TcGemmArgs {
   double* stats;
   float* db;
   StepBookkeeping bk;
+  unsigned long long* trace;   // timeline slot (diagnostics) or nullptr
 };
 
 // ---- thread-block cluster helpers (split-K reduction through distributed shared memory) ----
@@ -228,6 +229,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
   pdl_wait();
   pdl_launch_dependents();
+  trace_begin(g.trace);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -499,6 +501,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
   fence_before_thread_sync();
   __syncthreads();
+  trace_end(g.trace);
   if (warp == 1) {
     fence_after_thread_sync();
     tmem_dealloc(tmem_base, BN);
@@ -572,6 +575,7 @@ struct GemmCall {
   bool c_is_zero;     // caller guarantees C is already zero (skips the split-K memset)
   // epi == 4: fused softmax / cross-entropy / dZ epilogue of the output layer (C is not written)
   const int32_t* labels; float* dz; int64_t lddz; double* stats; float* db; StepBookkeeping bk;
+  int max_ctas;       // > 0: cap tiles x split (a GEMM meant to run on the SMs another kernel leaves idle)
 };
 
 // how many clusters of S CTAs (S = 2, 4, 8 -> slot 0, 1, 2) of each instantiation the device can hold at once;
@@ -670,6 +674,7 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
     split = (int)std::min<int64_t>(c->num_sms / tiles, num_kb / 4);
     if (split < 1) split = 1;
   }
+  if (g.max_ctas > 0) split = std::max(1, std::min(split, g.max_ctas / std::max(1, tiles)));
   int kb_per_split = (int)ceil_div(num_kb, split);
   split = (int)ceil_div(num_kb, kb_per_split);  // no empty slices
   // When the output needs an epilogue (or is not known to be zero) the k-slices of a tile run as one thread-block
@@ -709,8 +714,10 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   a.cluster_reduce = cluster ? 1 : 0;
   a.pair = pair ? 1 : 0;
   a.labels = g.labels; a.dz = g.dz; a.lddz = g.lddz; a.stats = g.stats; a.db = g.db; a.bk = g.bk;
+  a.trace = trace_slot(c, g.cls);
   if (cluster) a.atomic = 0;
   dim3 grid(tiles_n, pair ? (unsigned)round_up(tiles_m, 2) : tiles_m, split);
+  c->last_gemm_ctas = (int)(grid.x * grid.y * grid.z);
   if (split > 1 && !g.c_is_zero && !cluster) {
     LaunchScope ls(c, g.cls);   // the split-K zero-fill and fix-up are part of this GEMM's cost
     PB_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * ((size_t)(g.M - 1) * g.ldc + g.N), c->stream));

@@ -593,7 +593,7 @@ def _epoch_run(lib, env, monkeypatch, mode, opt, n=2100, bs=128, epochs=2, S=32,
     """`epochs` epochs over n rows (short last batch) in a fresh context created under `env`; returns per-epoch
     (loss, correct) and the final parameters."""
     for k in ("PYCNN_B200_PREFETCH", "PYCNN_B200_GRAPH_STEPS", "PYCNN_B200_FUSE_SOFTMAX", "PYCNN_B200_CLUSTER_SPLITK",
-              "PYCNN_B200_FORK", "PYCNN_B200_FUSE_UPDATE", "PYCNN_B200_GRAPHS", "PYCNN_B200_CARVEOUT"):
+              "PYCNN_B200_FORK", "PYCNN_B200_FUSE_UPDATE", "PYCNN_B200_GRAPHS", "PYCNN_B200_CARVEOUT", "PYCNN_B200_DEFER_DW"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -619,8 +619,8 @@ def _epoch_run(lib, env, monkeypatch, mode, opt, n=2100, bs=128, epochs=2, S=32,
 
 
 @pytest.mark.parametrize("env", [{"PYCNN_B200_GRAPH_STEPS": "1"}, {"PYCNN_B200_GRAPH_STEPS": "4"}, {"PYCNN_B200_FORK": "0"},
-                                 {"PYCNN_B200_GRAPHS": "0"}, {"PYCNN_B200_FUSE_UPDATE": "1"}, {}],
-                         ids=["graph1", "graph4", "nofork", "eager", "fused_update", "default"])
+                                 {"PYCNN_B200_GRAPHS": "0"}, {"PYCNN_B200_FUSE_UPDATE": "1"}, {"PYCNN_B200_DEFER_DW": "0"}, {}],
+                         ids=["graph1", "graph4", "nofork", "eager", "fused_update", "nodefer", "default"])
 def test_step_scheduling_does_not_change_results(lib, monkeypatch, env):
     """Row-gather prefetch, multi-step graphs, fork/join and the fused norm+update only reschedule the step: two
     FP32 SGD epochs (17 batches each, short last one) give the plain one-stream path's losses and parameters."""
