@@ -451,12 +451,13 @@ int p2p_exchange_update(pycnn_b200_ctx* c) {
   {
     LaunchScope ls(c, KC_ALLREDUCE);
     PB_CUDA(launch_pdl(c, p2p::p2p_reduce_kernel, dim3(grid), dim3(256), 0, c->stream, t, (const Chunk*)c->d_chunks,
-                       (const long long*)c->d_p2p_seq, c->d_norm_part, (int)c->tensors.size(), c->d_blocks_done));
+                       (const long long*)c->d_p2p_seq, c->d_norm_part, (int)c->tensors.size(), c->d_blocks_done,
+                       trace_slot(c, KC_ALLREDUCE)));
   }
   UpdateParams u = make_update_params(c);
   LaunchScope ls(c, KC_UPDATE);
   PB_CUDA(launch_pdl(c, p2p::p2p_update_kernel, dim3(grid), dim3(256), 0, c->stream, t, (const Chunk*)c->d_chunks,
-                     c->d_p2p_seq, c->d_m, c->d_v, u, c->d_blocks_done + 1));
+                     c->d_p2p_seq, c->d_m, c->d_v, u, c->d_blocks_done + 1, trace_slot(c, KC_UPDATE)));
   return 0;
 }
 

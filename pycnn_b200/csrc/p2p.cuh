@@ -85,8 +85,10 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {
 __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chunk* __restrict__ chunks,
                                                          const long long* __restrict__ seq_ptr,
                                                          double* __restrict__ norm_part, int ntensors,
-                                                         unsigned int* __restrict__ blocks_done) {
+                                                         unsigned int* __restrict__ blocks_done,
+                                                         unsigned long long* trace) {
   pdl_wait();
+  trace_begin(trace);
   const unsigned long long seq = (unsigned long long)seq_ptr[1] + 1ull;   // exchanges completed since attach + 1
   if (blockIdx.x == 0 && threadIdx.x < t.world) {
     __threadfence_system();   // my backward pass (previous kernels of this stream) is visible system-wide
@@ -155,14 +157,17 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chun
     for (int k = threadIdx.x; k < ntensors; k += blockDim.x) norm_part[k] = 0.0;   // ready for the next step
     if (threadIdx.x == 0) *blocks_done = 0u;
   }
+  trace_end(trace);
 }
 
 // ---- C: sharded clip + update, all-gather of the new parameters ------------------------------------------
 __global__ void __launch_bounds__(256) p2p_update_kernel(PeerTable t, const Chunk* __restrict__ chunks,
                                                          long long* __restrict__ seq_ptr, float* __restrict__ m,
                                                          float* __restrict__ v, UpdateParams u,
-                                                         unsigned int* __restrict__ blocks_done) {
+                                                         unsigned int* __restrict__ blocks_done,
+                                                         unsigned long long* trace) {
   pdl_wait();
+  trace_begin(trace);
   const unsigned long long seq = (unsigned long long)seq_ptr[1] + 1ull;   // exchanges completed since attach + 1
   __shared__ double s_n2;
   if ((int)blockIdx.x < t.nchunks) {
@@ -241,6 +246,7 @@ __global__ void __launch_bounds__(256) p2p_update_kernel(PeerTable t, const Chun
     __syncthreads();
     if (threadIdx.x == 0) seq_ptr[1] = (long long)seq;   // every block of this launch has already read the old value
   }
+  trace_end(trace);
 }
 
 }  // namespace p2p

@@ -17,7 +17,14 @@ from pycnn_b200.pycnn import PyCNN
 
 S, C, LAYERS, BS, N = 32, 10, [256, 128, 64], 4096, 65536
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-ctx = lib.Context(0)
+rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+ctx = lib.Context(int(os.environ.get("LOCAL_RANK", "0")))
+if world > 1:      # torchrun: weak scaling like bench.py, peer-memory gradient exchange
+    from pycnn_b200 import parallel
+    parallel.init_process_group()
+    uid = parallel.broadcast_bytes(lib.comm_unique_id() if rank == 0 else None)
+    ctx.comm_init(uid, rank, world)
+    BS *= world
 ctx.set_math_mode(lib.MATH_TF32)
 ctx.set_filters(PyCNN().filters)
 D = ctx.feature_count(S)
@@ -28,6 +35,8 @@ for l in range(len(dims) - 1):
     ctx.set_param(2 * l, rng.standard_normal((dims[l + 1], dims[l])) * (2 / dims[l]) ** 0.5)
     ctx.set_param(2 * l + 1, rng.standard_normal(dims[l + 1]) * 0.01)
 ctx.set_optimizer(lib.OPT_ADAM, 1e-4)
+if world > 1:
+    parallel.attach_peer_memory(ctx, rank, world)      # needs the network's gradient / parameter buffers
 ctx.dataset_alloc(N)
 for s in range(0, N, 16384):
     ctx.dataset_extract(s, rng.integers(0, 256, (16384, S, S, 3), dtype=np.uint8))
@@ -43,6 +52,9 @@ ctx.event_record(1)
 ctx.synchronize()
 ms = ctx.event_elapsed_ms(0, 1)
 ev = ctx.trace_read()
+if rank != 0:
+    ctx.close()
+    sys.exit(0)
 print(f"# {steps} steps in {ms * 1e3:.1f} us = {ms * 1e3 / steps:.2f} us/step (CUDA events around train_epoch); "
       f"{len(ev)} traced launches")
 # a step starts at a layer-1 forward GEMM on the main stream
