@@ -201,3 +201,22 @@ def test_world2_gloo_sharded_training_equals_single_process(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "GLOO_OK" in res.stdout
+
+
+def test_checkpoint_sidecar_does_not_shadow_model_bin(tmp_path):
+    """the resumable checkpoint is a separate, tagged file; a reference-format model.bin is refused by
+    load_checkpoint before any device work (so this runs without a GPU) and the tag is what save_checkpoint writes."""
+    import pickle
+    from pycnn_b200 import PyCNN
+    m = PyCNN()
+    model_bin = tmp_path / "model.bin"
+    with open(model_bin, "wb") as f:
+        pickle.dump({"weights": {}, "biases": {}, "filters": m.filters, "image_size": 32, "classes": ["a"],
+                     "layers": [8], "trained_with_cuda": False}, f, protocol=4)
+    with pytest.raises(ValueError, match="checkpoint"):
+        m.load_checkpoint(str(model_bin))
+    assert PyCNN.CHECKPOINT_FORMAT.startswith("pycnn_b200.checkpoint/")
+    import inspect
+    sig = inspect.signature(PyCNN.train_model)
+    assert list(sig.parameters)[:3] == ["self", "visualize", "early_stop"]          # reference signature first (:572)
+    assert sig.parameters["start_epoch"].default == 0 and sig.parameters["checkpoint"].default is None
