@@ -663,6 +663,7 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
         tiles_m * (int)ceil_div(g.N, BN * 2) * 2 > c->num_sms)
       BN <<= 1;
   }
+  if (c->force_bn > 0 && num_kb > 16 && g.N >= c->force_bn) BN = c->force_bn;   // experiments (PYCNN_B200_FORCE_BN)
   const int tiles_n = (int)ceil_div(g.N, BN);
   // deep-K problems whose tile grid cannot fill the 148 SMs: split K across gridDim.z, partial sums meet in
   // red.global.add.v4.f32 (the epilogue is then applied by gemm_fixup_kernel)
