@@ -448,6 +448,16 @@ int p2p_exchange_update(pycnn_b200_ctx* c) {
   }
   t.rank = c->rank; t.world = c->world; t.chunk0 = c->p2p_chunk0; t.nchunks = c->p2p_nchunks;
   const int grid = std::max(1, c->p2p_nchunks);
+  // every rank must take the same branch: the decision depends only on the (identical) network and world size
+  const int max_owned = (int)ceil_div(c->num_chunks, c->world);
+  if (c->p2p_fused && max_owned <= 2 * c->num_sms) {     // whole grid co-resident even beside the prefetch gather
+    UpdateParams u = make_update_params(c);
+    LaunchScope ls(c, KC_ALLREDUCE);
+    PB_CUDA(launch_pdl(c, p2p::p2p_fused_kernel, dim3(grid), dim3(256), 0, c->stream, t, (const Chunk*)c->d_chunks,
+                       c->d_p2p_seq, c->d_norm_part, (int)c->tensors.size(), c->d_m, c->d_v, u, c->d_blocks_done,
+                       trace_slot(c, KC_ALLREDUCE)));
+    return 0;
+  }
   {
     LaunchScope ls(c, KC_ALLREDUCE);
     PB_CUDA(launch_pdl(c, p2p::p2p_reduce_kernel, dim3(grid), dim3(256), 0, c->stream, t, (const Chunk*)c->d_chunks,
@@ -792,6 +802,7 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_FORK"); if (g && g[0] == '0') { cudaStreamDestroy(c->side_stream); c->side_stream = nullptr; } }
   { const char* g = getenv("PYCNN_B200_CARVEOUT"); if (g && g[0] == '0') c->uniform_carveout = false; }
   { const char* g = getenv("PYCNN_B200_FORCE_BN"); if (g && (atoi(g) == 64 || atoi(g) == 128 || atoi(g) == 256)) c->force_bn = atoi(g); }
+  { const char* g = getenv("PYCNN_B200_P2P_FUSED"); if (g) c->p2p_fused = (g[0] == '1'); }
   { const char* g = getenv("PYCNN_B200_DEFER_DW"); if (g && g[0] == '0') c->defer_last_dw = false; }
   { const char* g = getenv("PYCNN_B200_GRAPH_STEPS"); if (g && atoi(g) > 0) c->graph_steps = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PF_CTAS"); if (g && atoi(g) > 0) c->pf_ctas_per_sm = atoi(g); }
@@ -819,6 +830,7 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
     prefer((const void*)gather_rows_kernel); prefer((const void*)softmax_ce_kernel); prefer((const void*)grad_sqnorm_kernel);
     prefer((const void*)clip_update_kernel); prefer((const void*)norm_clip_update_kernel); prefer((const void*)gemm_fixup_kernel); prefer((const void*)step_bookkeeping_kernel);
     prefer((const void*)colsum_kernel); prefer((const void*)p2p::p2p_reduce_kernel); prefer((const void*)p2p::p2p_update_kernel);
+    prefer((const void*)p2p::p2p_fused_kernel);
     if (e != cudaSuccess) { fail("cudaFuncSetAttribute(carve-out) failed: %s", cudaGetErrorString(e)); return bail(1); }
   }
   if (tc_gemm_prepare(c) != 0 || tc_extract_prepare(c) != 0) return bail(1);

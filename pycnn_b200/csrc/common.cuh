@@ -125,6 +125,7 @@ struct pycnn_b200_ctx {
   unsigned long long* d_trace = nullptr;
   int trace_cap = 0, trace_next = 0;
   std::vector<int> trace_cls;          // kernel class of each slot, + 100 x stream id (0 main, 1 side, 2 prefetch)
+  bool p2p_fused = false;              // reduce-scatter + norms + update + all-gather in ONE launch (PYCNN_B200_P2P_FUSED=1)
   int force_bn = 0;                    // PYCNN_B200_FORCE_BN: tile width override for deep-K GEMMs (experiments)
   int last_gemm_ctas = 0;              // grid size of the most recent tensor-core GEMM launch
   bool defer_last_dw = true;           // backward: dW of layer 2 runs on the SMs dW of layer 1 leaves idle (PYCNN_B200_DEFER_DW=0)
