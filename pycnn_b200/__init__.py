@@ -7,5 +7,12 @@ include/pycnn_b200.h); importing this package does not need a GPU, using it does
 """
 from .pycnn import DeviceFeatures, Evaluate, PyCNN  # noqa: F401
 
-__all__ = ["PyCNN", "Evaluate", "DeviceFeatures"]
+__all__ = ["PyCNN", "Evaluate", "DeviceFeatures", "PyCNNTorchModel"]
 __version__ = "0.1.0"
+
+
+def __getattr__(name):   # PyCNNTorchModel needs torch: resolved on first use only
+    if name == "PyCNNTorchModel":
+        from . import torch_export
+        return torch_export.PyCNNTorchModel
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -535,6 +535,15 @@ class PyCNN:
         if trained_with_cuda != self.use_cuda:
             print("Backend conversion completed automatically.")
 
+    def torch(self, path="model.pth", dtype=None):
+        """Export to the PyTorch checkpoint the reference documents (README.md:184-250)."""
+        from . import torch_export
+        if self.use_cuda and self._ctx is not None and self._params_on_device:
+            self._pull_params()
+        net = torch_export.export(self, path, dtype=dtype)
+        print(f"PyTorch model exported to {path}")
+        return net
+
     # ------------------------------------------------------------------ resumable checkpoints (SURVEY 8f-3)
     CHECKPOINT_FORMAT = "pycnn_b200.checkpoint/1"
 
@@ -761,3 +770,10 @@ class Evaluate:
         for name, s in stats.items():
             print(name + ":", str(s["correct"]) + "/" + str(s["total"]))
         self.last_result = {"acc": correct / n, "loss": loss_sum / n, "per_class": stats}
+
+
+def __getattr__(name):   # `from pycnn_b200.pycnn import PyCNNTorchModel`, as the reference README imports it
+    if name == "PyCNNTorchModel":
+        from . import torch_export
+        return torch_export.PyCNNTorchModel
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
