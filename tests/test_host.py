@@ -40,7 +40,9 @@ def test_library_is_sm100a_tcgen05_tma():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass or "SM100" in sass.upper()
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+    # tcgen05.mma / TMA tensor loads / tcgen05.ld, plus what the cluster paths compile to: multicast TMA loads and
+    # multicast tcgen05.commit (paired CTAs), cluster barriers (DSMEM split-K), TMA 1-D bulk copies (extractor)
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTMALDG.2D.MULTICAST", "UTCBAR.MULTICAST", "UCGABAR_ARV", "UBLKCP"):
         assert mnemonic in sass, mnemonic
 
 
