@@ -44,6 +44,41 @@ def _default_filters():
     return [[list(row) for row in f] for f in _DEFAULT_FILTERS]
 
 
+def _decode_files(paths, image_size, limit=None, on_ok=None, on_fail=None, workers=None):
+    """Decode + RGB-convert + LANCZOS-resize image files on host threads (PIL releases the GIL while it decodes and
+    resamples), keeping the reference's sequential semantics (pycnn/pycnn.py:355-372): files are taken in listing
+    order, a file that fails is reported and skipped, and at most `limit` SUCCESSFUL images are kept.  Work is issued
+    in windows of the number of images still wanted, so nothing beyond the limit is decoded needlessly.  Returns the
+    list of uint8 [S,S,3] arrays; on_ok(path, count) / on_fail(path, exc) are called in file order."""
+    from concurrent.futures import ThreadPoolExecutor
+    paths = list(paths)
+    if limit is not None and limit <= 0:
+        return []
+    workers = workers or min(32, (os.cpu_count() or 4))
+
+    def work(path):
+        try:
+            return _to_u8_image(path, image_size)
+        except Exception as e:          # reported by the caller, in order
+            return e
+
+    out, pos = [], 0
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        while pos < len(paths) and (limit is None or len(out) < limit):
+            want = len(paths) - pos if limit is None else min(len(paths) - pos, max(limit - len(out), 1))
+            window = paths[pos:pos + want]
+            pos += want
+            for path, res in zip(window, pool.map(work, window)):
+                if isinstance(res, Exception):
+                    if on_fail:
+                        on_fail(path, res)
+                    continue
+                out.append(res)
+                if on_ok:
+                    on_ok(path, len(out))
+    return out
+
+
 def _to_u8_image(obj, image_size=None):
     """Path -> PIL open/RGB/LANCZOS resize (pycnn/pycnn.py:269); anything else is taken as pixels (:271)."""
     if isinstance(obj, str):
@@ -265,18 +300,12 @@ class PyCNN:
                     if not files:
                         print(f"Warning: No image files found in {folder}")
                         continue
-                    count = 0
-                    for name in files:
-                        if max_image is not None and count >= max_image:
-                            break
-                        img_path = f"{folder}/{name}"
-                        print(f"\r\033[KLoading local dataset: {cls}/{name} ({count + 1})", end="", flush=True)
-                        try:
-                            images.append(_to_u8_image(img_path, image_size))
-                            label_idx.append(idx)
-                            count += 1
-                        except Exception as e:
-                            print(f"\nWarning: Failed to process {img_path}: {e}")
+                    got = _decode_files(
+                        [f"{folder}/{name}" for name in files], image_size, max_image,
+                        on_ok=lambda pth, n, cls=cls: print(f"\r\033[KLoading local dataset: {cls}/{os.path.basename(pth)} ({n})", end="", flush=True),
+                        on_fail=lambda pth, e: print(f"\nWarning: Failed to process {pth}: {e}"))
+                    images.extend(got)
+                    label_idx.extend([idx] * len(got))
                 print(f"\nLoaded {len(images)} images from {len(classes)} classes")
                 if not images:
                     raise ValueError("No images were successfully loaded")
@@ -683,17 +712,11 @@ class Evaluate:
             folder = os.path.join(path, cls)
             if not os.path.isdir(folder):
                 continue
-            count = 0
-            for name in [f for f in os.listdir(folder) if f.lower().endswith(_IMAGE_EXT_EVAL)]:
-                if max_image is not None and count >= max_image:
-                    break
-                img_path = os.path.join(folder, name)
-                try:
-                    images.append(_to_u8_image(img_path, m.image_size))
-                    label_idx.append(idx)
-                    count += 1
-                except Exception as e:
-                    print(f"\nWarning: Failed to process {img_path}: {e}")
+            names = [f for f in os.listdir(folder) if f.lower().endswith(_IMAGE_EXT_EVAL)]
+            got = _decode_files([os.path.join(folder, name) for name in names], m.image_size, max_image,
+                                on_fail=lambda pth, e: print(f"\nWarning: Failed to process {pth}: {e}"))
+            images.extend(got)
+            label_idx.extend([idx] * len(got))
         return self._run_images(images, label_idx)
 
     def hf(self, dataset_name, split="test", max_image=None):

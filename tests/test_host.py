@@ -222,3 +222,28 @@ def test_checkpoint_sidecar_does_not_shadow_model_bin(tmp_path):
     sig = inspect.signature(PyCNN.train_model)
     assert list(sig.parameters)[:3] == ["self", "visualize", "early_stop"]          # reference signature first (:572)
     assert sig.parameters["start_epoch"].default == 0 and sig.parameters["checkpoint"].default is None
+
+
+def test_threaded_decode_keeps_sequential_semantics(tmp_path):
+    """dataset ingest decodes on host threads but keeps the reference loop's meaning (pycnn.py:355-372):
+    listing order, failures reported and skipped, max_image counts successes only."""
+    from PIL import Image
+    from pycnn_b200.pycnn import _decode_files, _to_u8_image
+    rng = np.random.default_rng(3)
+    paths = []
+    for i in range(9):
+        pth = tmp_path / f"img_{i}.png"
+        if i in (1, 4):
+            pth.write_bytes(b"not an image")                    # undecodable files in the middle of the listing
+        else:
+            Image.fromarray(rng.integers(0, 256, (20 + i, 20 + i, 3), dtype=np.uint8), mode="RGB").save(pth)
+        paths.append(str(pth))
+    ok, bad = [], []
+    got = _decode_files(paths, 16, limit=5, on_ok=lambda p, n: ok.append((os.path.basename(p), n)),
+                        on_fail=lambda p, e: bad.append(os.path.basename(p)), workers=4)
+    assert [o[0] for o in ok] == ["img_0.png", "img_2.png", "img_3.png", "img_5.png", "img_6.png"]
+    assert [o[1] for o in ok] == [1, 2, 3, 4, 5] and bad == ["img_1.png", "img_4.png"]
+    assert len(got) == 5 and all(g.shape == (16, 16, 3) and g.dtype == np.uint8 for g in got)
+    for g, name in zip(got, [o[0] for o in ok]):
+        np.testing.assert_array_equal(g, _to_u8_image(str(tmp_path / name), 16))    # same pixels as the sequential path
+    assert len(_decode_files(paths, 16)) == 7 and _decode_files(paths, 16, limit=0) == []
