@@ -1,6 +1,6 @@
 """Side measurements for the other BASELINE.json configurations (bench.py's JSON line is configs[1]).
 
-    python scripts/bench_configs.py [c1] [c3] [c4] [c5]
+    python scripts/bench_configs.py [c1] [c3] [c4] [c5] [c5f19]
 
 c1  32x32, 10 classes, [256,128,64], batch 32, SGD                      -> launch-latency-bound step
 c3  64x64, 100 classes, [1024,512,256], Adam, batch 4096                -> tensor-bound step
@@ -133,6 +133,8 @@ if __name__ == "__main__":
             print(json.dumps(train_config("c3", 64, 100, [1024, 512, 256], 4096, "adam", 1e-4, 16384, 20)), flush=True)
         elif w == "c4":
             print(json.dumps(config4()), flush=True)
+        elif w == "c5f19":   # configs[4] with the default 19-filter bank: D = 234 099, 482 M parameters (1.93 GB f32)
+            print(json.dumps(train_config("c5f19", 224, 1000, [2048, 1024, 512], 512, "adam", 1e-4, 1024, 6)), flush=True)
         elif w == "c5":
             print(json.dumps(train_config("c5", 224, 1000, [2048, 1024, 512], 512, "adam", 1e-4, 2048, 10,
                                           filters=custom_filters(8))), flush=True)
