@@ -246,7 +246,7 @@ def test_cupy_update_rule_and_nan_skip(lib, ctx):
 # float64 reference to storage precision.  The reference's CPU Adam keeps t frozen at 1, which
 # makes the update nearly sign-like (lr * m_hat / sqrt(v_hat) ~ +-lr for small gradients), so rounding noise is
 # amplified chaotically: a plain numpy float32 restatement of the reference deviates by 3.0e-2 and a numpy
-# emulation of TF32 operand rounding by 1.7e-1 on this exact run (scripts/precision_study.py; repeated TF32 runs of
+# emulation of TF32 operand rounding by 1.7e-1 on this exact run (tests/tools/precision_study.py; repeated TF32 runs of
 # the CUDA path scatter between 1.2e-1 and 3.1e-1 because split-K partial sums meet in atomic order).  The CUDA path
 # must stay inside those envelopes; it cannot be tighter than the arithmetic it is specified to use.
 TRAJ_TOL = {("fp32", "sgd"): 1e-5, ("fp32", "adam"): 5e-2, ("tf32", "sgd"): 5e-2, ("tf32", "adam"): 5e-1}

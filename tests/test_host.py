@@ -247,3 +247,34 @@ def test_threaded_decode_keeps_sequential_semantics(tmp_path):
     for g, name in zip(got, [o[0] for o in ok]):
         np.testing.assert_array_equal(g, _to_u8_image(str(tmp_path / name), 16))    # same pixels as the sequential path
     assert len(_decode_files(paths, 16)) == 7 and _decode_files(paths, 16, limit=0) == []
+
+
+def test_oracle_is_test_infrastructure_only():
+    """The oracle is the checker, never the product: nothing under pycnn_b200/ or scripts/ imports it, bench.py only
+    in its cpu_baseline / --impl reference legs, __graft_entry__ only in build() (builds the checker) and smoke()."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def oracle_imports(path):
+        tree = ast.parse(open(path).read())
+        hits = []
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in node.names):
+                hits.append(node.lineno)
+            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
+                hits.append(node.lineno)
+        return hits
+
+    for sub in ("pycnn_b200", "scripts"):
+        for dirpath, _, files in os.walk(os.path.join(root, sub)):
+            for f in files:
+                if f.endswith(".py"):
+                    assert not oracle_imports(os.path.join(dirpath, f)), f"{sub}/{f} imports the oracle"
+    # bench.py: module level must be oracle-free; the imports live inside the CPU-baseline helpers
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert not any(isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle") for n in top)
+    assert not any(isinstance(n, ast.Import) and any(a.name.startswith("oracle") for a in n.names) for n in top)
+    fn_with_oracle = {n.name for n in tree.body if isinstance(n, ast.FunctionDef)
+                      for m in ast.walk(n) if isinstance(m, ast.ImportFrom) and (m.module or "").startswith("oracle")}
+    assert fn_with_oracle and all("cpu" in name or "reference" in name for name in fn_with_oracle), fn_with_oracle

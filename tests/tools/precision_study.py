@@ -2,7 +2,7 @@
 reference over the 100-step BASELINE config-1 run (tests/golden/traj_c1.npz).  Pure numpy; test
 infrastructure (imports oracle/).  Results are quoted in DESIGN.md and tests/test_gpu_parity.py."""
 import numpy as np, sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pycnn_oracle as O
 from tests.helpers import load_golden, synth_images, synth_labels
 g = load_golden("traj_c1.npz")
