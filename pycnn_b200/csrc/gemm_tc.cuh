@@ -469,11 +469,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int o = LPR; o < 32; o <<= 1) cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], o);
         }
-        if (lr == 0 && col_ok && nrows > 0) {
+        // per-warp sums meet in smem (behind the staging tiles) first: one global atomic per column per CTA instead
+        // of four -- the same-address atomics of 32 M-tiles x 4 warps were a 2-4 us completion tail of the dA GEMMs
+        if (lr == 0 && col_ok) {
+          float* cs_smem = reinterpret_cast<float*>(smem) + 128 * PITCH + q * BN + cc;
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (n + e < g.N) atomicAdd(g.colsum + n + e, cs[e]);
+          for (int e = 0; e < 4; ++e) cs_smem[e] = cs[e];       // rows past M contributed nothing: zeros
         }
+      }
+    }
+    if (g.colsum && !g.atomic) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
+      const float* cs_all = reinterpret_cast<const float*>(smem) + 128 * PITCH;
+      for (int j = (warp - 2) * 32 + lane; j < ncols; j += 128) {
+        const float tot = (cs_all[j] + cs_all[BN + j]) + (cs_all[2 * BN + j] + cs_all[3 * BN + j]);
+        if (n0 + j < g.N) atomicAdd(g.colsum + n0 + j, tot);
       }
     }
     }  // !cluster_reduce
