@@ -278,3 +278,27 @@ def test_oracle_is_test_infrastructure_only():
     fn_with_oracle = {n.name for n in tree.body if isinstance(n, ast.FunctionDef)
                       for m in ast.walk(n) if isinstance(m, ast.ImportFrom) and (m.module or "").startswith("oracle")}
     assert fn_with_oracle and all("cpu" in name or "reference" in name for name in fn_with_oracle), fn_with_oracle
+
+
+def test_committed_bench_line_honours_the_contract():
+    """The JSON line bench.py printed on the B200 (profiles/r1_bench_1gpu.json) carries every key the driver reads."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = open(os.path.join(root, "profiles", "r1_bench_1gpu.json")).read().strip().splitlines()[-1]
+    d = json.loads(line)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["metric"] == "train_images_per_sec" and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["data"] == "synthetic" and d["dtype"] == "tf32"
+    assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and "workload" in d["config"] and "l2" in d["config"]
+    assert abs(d["value"] - d["steps"] * d["config"]["global_batch"] / (d["ms_per_step"] * d["steps"] / 1e3)) < 1e-6 * d["value"]
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["unit"] == d["unit"] and c["sample"]
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
