@@ -384,7 +384,31 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
+class all_host_threads:
+    """Give the CPU arm every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, which would pin the
+    reference's BLAS to one thread and flatter the GPU arm."""
+
+    def __enter__(self):
+        self._ctl = None
+        try:
+            from threadpoolctl import threadpool_limits
+            self._ctl = threadpool_limits(limits=os.cpu_count() or 1)
+        except Exception:
+            pass
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctl is not None:
+            self._ctl.restore_original_limits()
+        return False
+
+
 def cpu_baseline(seconds=12.0):
+    with all_host_threads():
+        return _cpu_baseline(seconds)
+
+
+def _cpu_baseline(seconds):
     kind, step = make_cpu_trainer(BS)
     step()
     n, t0 = 0, time.perf_counter()
@@ -406,15 +430,17 @@ def run_reference(args):
     if rank != 0:
         return
     gbs = BS * world
-    kind, step = make_cpu_trainer(gbs)
-    for _ in range(max(1, min(args.warmup, 3))):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    el = time.perf_counter() - t0
+    with all_host_threads():
+        kind, step = make_cpu_trainer(gbs)
+        for _ in range(max(1, min(args.warmup, 3))):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        el = time.perf_counter() - t0
+        threads = cpu_threads()
     value = args.steps * gbs / el
-    cb = {"value": value, "unit": "images/s", "cores": cpu_threads(), "kind": kind,
+    cb = {"value": value, "unit": "images/s", "cores": threads, "kind": kind,
           "sample": f"{args.steps} CPU train steps of batch {gbs}; os.cpu_count()={os.cpu_count()}"}
     print(json.dumps({
         "impl": "reference", "metric": "train_images_per_sec", "value": value, "unit": "images/s",
