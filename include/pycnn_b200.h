@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PYCNN_B200_ABI_VERSION 1
+#define PYCNN_B200_ABI_VERSION 2
 
 typedef struct pycnn_b200_ctx pycnn_b200_ctx;
 
@@ -140,10 +140,12 @@ int pycnn_b200_train_step_images(pycnn_b200_ctx* ctx, const uint8_t* images, con
  * order) are brought to the device on a copy stream -- copy engine for contiguous batches, a zero-copy gather
  * kernel over PCIe for permuted rows of pinned/registered memory -- double-buffered against extractor + step on
  * the compute stream; the running (loss, #correct) totals are read back asynchronously after every step.
- * step_stats (nullable) receives 2 doubles per step: cumulative loss sum and cumulative #correct. */
+ * step_stats (nullable) receives 2 doubles per step: cumulative loss sum and cumulative #correct.
+ * images / labels hold num_images rows; the epoch trains n rows: perm[0..n) with every entry in
+ * [0, num_images) (checked on the host before anything is launched), or rows 0..n-1 (n <= num_images). */
 int pycnn_b200_train_epoch_images(pycnn_b200_ctx* ctx, const uint8_t* images, const int32_t* labels,
-                                  const int64_t* perm, int64_t n, int image_size, int batch_size,
-                                  double* step_stats, double* loss_sum, int64_t* correct);
+                                  int64_t num_images, const int64_t* perm, int64_t n, int image_size,
+                                  int batch_size, double* step_stats, double* loss_sum, int64_t* correct);
 /* `steps` back-to-back steps on dataset rows idx[s*bs .. (s+1)*bs), no host sync inside
  * (device-resident benchmark loop); outputs are totals over the steps. */
 int pycnn_b200_train_steps(pycnn_b200_ctx* ctx, const int64_t* idx, int bs, int steps,
@@ -181,11 +183,14 @@ int pycnn_b200_comm_destroy(pycnn_b200_ctx* ctx);
  * reduce-scatter -> norms -> sharded clip/Adam -> all-gather over NVLink peer pointers.  Every rank exports
  * the CUDA IPC handles of its gradient, parameter and sync buffers (192 bytes, after set_network), the host
  * layer all-gathers them, and every rank attaches to all `world` blobs (rank order).  world <= 8, one node.
- * set_network / comm_destroy detach.  Adam m, v are then sharded: a rank only holds state for its range. */
+ * set_network / comm_destroy detach.  Adam m, v are then sharded: a rank only holds state for its range until
+ * comm_sync_opt_state (a collective: every rank calls it) assembles the shards on every rank -- call it before
+ * get_opt_state / a checkpoint; comm_ipc_detach does it itself. */
 #define PYCNN_B200_IPC_BLOB_BYTES 192
 int pycnn_b200_comm_ipc_export(pycnn_b200_ctx* ctx, char* blob192);
 int pycnn_b200_comm_ipc_attach(pycnn_b200_ctx* ctx, const char* blobs, int rank, int world);
 int pycnn_b200_comm_ipc_detach(pycnn_b200_ctx* ctx);
+int pycnn_b200_comm_sync_opt_state(pycnn_b200_ctx* ctx);
 /* device pointer + element count of the flat float32 gradient buffer (for an external
  * all-reduce, e.g. torch.distributed on a wrapped tensor); valid until set_network */
 int pycnn_b200_grad_buffer(pycnn_b200_ctx* ctx, void** device_ptr, int64_t* num_floats);

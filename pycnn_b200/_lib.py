@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpycnn_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pycnn_b200.h")
 
+ABI_VERSION = 2          # include/pycnn_b200.h: PYCNN_B200_ABI_VERSION
 MATH_FP32_SIMT, MATH_TF32 = 0, 1
 RULE_CPU, RULE_CUPY = 0, 1
 OPT_SGD, OPT_ADAM = 0, 1
@@ -72,7 +73,7 @@ _SIGNATURES = {
     "pycnn_b200_train_epoch": [c_ctx, _i64p, I64, I, _dp, _i64p],
     "pycnn_b200_train_step_images": [c_ctx, ctypes.c_void_p, ctypes.c_void_p, I, I, _dp, _i64p],
     "pycnn_b200_train_steps": [c_ctx, _i64p, I, I, _dp, _i64p],
-    "pycnn_b200_train_epoch_images": [c_ctx, ctypes.c_void_p, ctypes.c_void_p, _i64p, I64, I, I, _dp, _dp, _i64p],
+    "pycnn_b200_train_epoch_images": [c_ctx, ctypes.c_void_p, ctypes.c_void_p, I64, _i64p, I64, I, I, _dp, _dp, _i64p],
     "pycnn_b200_forward_rows": [c_ctx, _i64p, I64, I, _dp],
     "pycnn_b200_forward_features": [c_ctx, _dp, I, _dp],
     "pycnn_b200_predict_images": [c_ctx, ctypes.c_void_p, I64, I, _i32p, _fp],
@@ -85,6 +86,7 @@ _SIGNATURES = {
     "pycnn_b200_comm_ipc_export": [c_ctx, ctypes.c_char_p],
     "pycnn_b200_comm_ipc_attach": [c_ctx, ctypes.c_char_p, I, I],
     "pycnn_b200_comm_ipc_detach": [c_ctx],
+    "pycnn_b200_comm_sync_opt_state": [c_ctx],
     "pycnn_b200_grad_buffer": [c_ctx, ctypes.POINTER(ctypes.c_void_p), _i64p],
     "pycnn_b200_forward_backward": [c_ctx, _i64p, I],
     "pycnn_b200_apply_update": [c_ctx],
@@ -129,6 +131,9 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, ctypes.c_int)
+    if lib.pycnn_b200_abi_version() != ABI_VERSION:
+        raise BackendError(f"{LIB_PATH} has ABI v{lib.pycnn_b200_abi_version()}, this binding needs v{ABI_VERSION}: "
+                           "rebuild with `make -C pycnn_b200/csrc`")
     _lib = lib
     return lib
 
@@ -385,8 +390,10 @@ class Context:
                                                     ctypes.byref(corr) if want_stats else None))
         return (loss.value, corr.value) if want_stats else None
 
-    def train_epoch_images(self, images_ptr, labels_ptr, n, size, batch_size, perm=None, want_step_stats=False):
-        """Streaming epoch from host memory (raw pointers so pinned buffers pass through untouched)."""
+    def train_epoch_images(self, images_ptr, labels_ptr, n, size, batch_size, perm=None, want_step_stats=False,
+                           num_images=None):
+        """Streaming epoch from host memory (raw pointers so pinned buffers pass through untouched).  The buffers
+        hold `num_images` rows (default n); perm entries are validated against it before anything is launched."""
         steps = -(-int(n) // int(batch_size))
         st = np.empty((steps, 2), dtype=np.float64) if want_step_stats else None
         if perm is not None:
@@ -394,7 +401,7 @@ class Context:
             assert perm.shape[0] == n
         loss, corr = ctypes.c_double(), ctypes.c_int64()
         check(self.lib.pycnn_b200_train_epoch_images(
-            self.handle, ctypes.c_void_p(images_ptr), ctypes.c_void_p(labels_ptr),
+            self.handle, ctypes.c_void_p(images_ptr), ctypes.c_void_p(labels_ptr), int(n if num_images is None else num_images),
             ptr(perm, ctypes.c_int64) if perm is not None else None, int(n), int(size), int(batch_size),
             ptr(st, ctypes.c_double) if st is not None else None, ctypes.byref(loss), ctypes.byref(corr)))
         return (loss.value, corr.value, st) if want_step_stats else (loss.value, corr.value)
@@ -478,6 +485,10 @@ class Context:
 
     def comm_ipc_detach(self):
         check(self.lib.pycnn_b200_comm_ipc_detach(self.handle))
+
+    def comm_sync_opt_state(self):
+        """Collective: assemble the sharded Adam m, v of the peer-memory mode on every rank (no-op otherwise)."""
+        check(self.lib.pycnn_b200_comm_sync_opt_state(self.handle))
 
     def grad_buffer(self):
         p, n = ctypes.c_void_p(), ctypes.c_int64()

@@ -6,7 +6,6 @@
 #include "elementwise.cuh"
 #include "extract_tc.cuh"
 #include "gemm_tc.cuh"
-#include "mlp_tail.cuh"
 #include "p2p.cuh"
 #include "simt.cuh"
 
@@ -27,6 +26,9 @@ int alloc_f32(float** p, int64_t n) {
 void free_dev(void* p) {
   if (p) cudaFree(p);
 }
+
+const TensorDesc& Wt(const pycnn_b200_ctx* c, int l) { return c->tensors[2 * l]; }
+const TensorDesc& Bt(const pycnn_b200_ctx* c, int l) { return c->tensors[2 * l + 1]; }
 
 int grid_for(int64_t total, int threads, int num_sms) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, threads), (int64_t)num_sms * 16));
@@ -50,13 +52,17 @@ int gemm(pycnn_b200_ctx* c, const GemmCall& g) {
     sgemm_simt_kernel<<<grid, 256, 0, c->stream>>>(a);
     PB_CUDA(cudaGetLastError());
   }
-  if (g.colsum) {   // the tensor-core kernel fuses this into its epilogue
+  if (g.grad_slot) c->gp[g.grad_slot - 1].nparts = 0;   // unsplit: C is the flat gradient buffer itself
+  if (g.colsum_slot) {   // the tensor-core kernel fuses this into its epilogue
+    GradPartSlot& gs = c->gp[g.colsum_slot - 1];
     const int col_blocks = (int)ceil_div(g.N, 32);
-    const int chunks = std::max(1, std::min((int)ceil_div(g.M, 64), (2 * c->num_sms + col_blocks - 1) / col_blocks));
+    const int chunks = std::max(1, std::min({(int)ceil_div(g.M, 64), (2 * c->num_sms + col_blocks - 1) / col_blocks, gs.cap}));
     const int rows_per_block = (int)ceil_div(g.M, chunks);
     dim3 cgrid((unsigned)col_blocks, (unsigned)ceil_div(g.M, rows_per_block));
+    PB_CHECK((int)cgrid.y <= gs.cap, "bias-gradient partial arena too small (%d row chunks, cap %d)", (int)cgrid.y, gs.cap);
+    gs.nparts = (int)cgrid.y;
     LaunchScope ls(c, KC_COLSUM);
-    colsum_kernel<<<cgrid, dim3(32, 8), 0, c->stream>>>(g.C, g.M, g.N, g.ldc, g.colsum, rows_per_block, 1);
+    colsum_kernel<<<cgrid, dim3(32, 8), 0, c->stream>>>(g.C, g.M, g.N, g.ldc, c->d_gpart + gs.off, gs.stride, rows_per_block);
     PB_CUDA(cudaGetLastError());
   }
   return 0;
@@ -66,6 +72,9 @@ int gemm(pycnn_b200_ctx* c, const GemmCall& g) {
 // workspace
 // ---------------------------------------------------------------------------------------------
 void free_workspace(pycnn_b200_ctx* c) {
+  free_dev(c->d_gpart); c->d_gpart = nullptr; c->gpart_floats = 0;
+  free_dev(c->d_gemm_ws); c->d_gemm_ws = nullptr; c->gemm_ws_bytes = 0;
+  for (auto& g : c->gp) g = GradPartSlot{};
   free_dev(c->d_blabels); c->d_blabels = nullptr;
   free_dev(c->d_x); c->d_x = nullptr;
   free_dev(c->d_x2); c->d_x2 = nullptr;
@@ -96,6 +105,28 @@ int ensure_workspace(pycnn_b200_ctx* c, int64_t bs) {
   PB_TRY(alloc_f32(&c->d_probs, cap * c->ldw[c->L + 1]));
   PB_CUDA(cudaMalloc(&c->d_pred, sizeof(int32_t) * cap));
   PB_CUDA(cudaMalloc(&c->d_conf, sizeof(float) * cap));
+  // Ordered-partial-sum arena: per weight tensor as many slices as its dW GEMM can be split into at this batch capacity
+  // (the split grows with K = batch rows), per bias one partial per row tile / softmax block / column-sum chunk.
+  int64_t off = 0;
+  for (int l = 0; l <= c->L; ++l) {
+    GemmCall g{};
+    g.a_kmajor = false; g.b_kmajor = false;
+    g.M = (int)c->dims[l + 1]; g.N = (int)c->dims[l]; g.K = (int)cap; g.grad_slot = 2 * l + 1;
+    const GemmPlan p = plan_tc_gemm(c, g);
+    GradPartSlot& w = c->gp[2 * l];
+    w.off = off; w.stride = Wt(c, l).rows * Wt(c, l).ld; w.cap = p.split > 1 ? p.split : 0; w.nparts = 0;
+    off = round_up(off + w.stride * w.cap, 64);
+    GradPartSlot& b = c->gp[2 * l + 1];
+    b.off = off; b.stride = Bt(c, l).ld; b.nparts = 0;
+    b.cap = (int)std::max<int64_t>(round_up(ceil_div(cap, tc::G_BM), 2), 2 * c->num_sms);
+    off = round_up(off + b.stride * b.cap, 64);
+  }
+  PB_TRY(alloc_f32(&c->d_gpart, off));
+  c->gpart_floats = off;
+  // shared workspace of split-K GEMMs with an epilogue whose slices cannot meet in distributed shared memory:
+  // tiles x slices never exceeds the SM count and a slice of a tile is at most 128 x 256 floats
+  c->gemm_ws_bytes = sizeof(float) * (size_t)(c->num_sms + 4) * 128 * 256;
+  PB_CUDA(cudaMalloc(&c->d_gemm_ws, c->gemm_ws_bytes));
   c->bs_cap = cap;
   return 0;
 }
@@ -178,31 +209,35 @@ int extract_device(pycnn_b200_ctx* c, const uint8_t* d_images, int64_t n, int S,
 // ---------------------------------------------------------------------------------------------
 // forward / backward / update on the batch currently in c->d_x (or an external x) and c->d_blabels
 // ---------------------------------------------------------------------------------------------
-const TensorDesc& Wt(const pycnn_b200_ctx* c, int l) { return c->tensors[2 * l]; }
-const TensorDesc& Bt(const pycnn_b200_ctx* c, int l) { return c->tensors[2 * l + 1]; }
 
 int issue_prefetch(pycnn_b200_ctx* c);
 
-// Gradient buffers are zeroed once per step: split-K dW partial sums and the fused bias-gradient column sums
-// (output-layer epilogue / softmax kernel, dA-GEMM epilogues) accumulate into them.  Inside a training step the
-// memset runs on the side stream beside the hidden-layer forward GEMMs and is joined before the first writer.
-int zero_grads(pycnn_b200_ctx* c, bool may_fork = false) {
-  LaunchScope ls(c, KC_MISC);
-  if (may_fork && !c->timing && c->side_stream) {
-    PB_CUDA(cudaEventRecord(c->ev_fork[0], c->stream));
-    PB_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork[0], 0));
-    PB_CUDA(cudaMemsetAsync(c->d_grads, 0, sizeof(float) * c->P, c->side_stream));
-    PB_CUDA(cudaEventRecord(c->ev_zero, c->side_stream));
-    c->zero_pending = true;
-    return 0;
+// Gradients are never accumulated with atomics and the flat gradient buffer is never zero-filled: every producer
+// either writes a tensor's gradient whole or stores ordered partial sums (GradPartSlot) that finalize_grads adds in
+// index order -- training is bit-reproducible.  begin_grads forgets the previous step's partial counts.
+void begin_grads(pycnn_b200_ctx* c) {
+  for (size_t t = 0; t < c->tensors.size(); ++t) c->gp[t].nparts = 0;
+}
+
+// partial sums -> flat gradient buffer (+ per-chunk sums of squares for the clip when want_norm)
+int finalize_grads(pycnn_b200_ctx* c, bool want_norm) {
+  GradParts gp{};
+  gp.base = c->d_gpart;
+  bool any = want_norm;
+  for (size_t t = 0; t < c->tensors.size(); ++t) {
+    gp.off[t] = c->gp[t].off; gp.stride[t] = c->gp[t].stride; gp.nparts[t] = c->gp[t].nparts;
+    any = any || c->gp[t].nparts > 0;
   }
-  PB_CUDA(cudaMemsetAsync(c->d_grads, 0, sizeof(float) * c->P, c->stream));
+  if (!any) return 0;
+  LaunchScope ls(c, KC_SQNORM);
+  PB_CUDA(launch_pdl(c, grad_finalize_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, c->d_grads,
+                     (const Chunk*)c->d_chunks, gp, c->d_chunk_norm, want_norm ? 1 : 0, trace_slot(c, KC_SQNORM)));
   return 0;
 }
-int join_zero_grads(pycnn_b200_ctx* c) {
-  if (!c->zero_pending) return 0;
-  c->zero_pending = false;
-  PB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_zero, 0));
+
+int zero_grads(pycnn_b200_ctx* c) {   // a rank whose shard of the batch is empty contributes zeros
+  LaunchScope ls(c, KC_MISC);
+  PB_CUDA(cudaMemsetAsync(c->d_grads, 0, sizeof(float) * c->P, c->stream));
   return 0;
 }
 
@@ -213,7 +248,7 @@ bool softmax_fusable(const pycnn_b200_ctx* c) {
 
 // x: [bs, Dp].  Leaves hidden activations in d_act and logits in d_probs (pitch ldw[L+1]).
 // train_labels != nullptr (only with softmax_fusable): the last GEMM runs the fused softmax/CE epilogue instead of
-// writing logits -- dZ_out lands in d_dz[L], loss/#correct in d_stats, db_o in the (zeroed) gradient buffer.
+// writing logits -- dZ_out lands in d_dz[L], loss/#correct in d_stats, db_o as ordered partials (one per row tile).
 int forward_logits(pycnn_b200_ctx* c, const float* x, int bs, const int32_t* train_labels = nullptr, int64_t advance = 0) {
   const float* in = x;
   for (int l = 0; l <= c->L; ++l) {
@@ -223,15 +258,14 @@ int forward_logits(pycnn_b200_ctx* c, const float* x, int bs, const int32_t* tra
     g.M = bs; g.N = (int)c->dims[l + 1]; g.K = (int)c->dims[l];
     g.bias = c->d_params + Bt(c, l).off;
     g.cls = (l == 0) ? KC_GEMM_FWD1 : KC_GEMM_FWD;
-    if (l == c->L) PB_TRY(join_zero_grads(c));   // first writer of the gradient buffer (db_o) comes next
     if (l < c->L) { g.C = c->d_act[l]; g.epi = 2; }
     else          { g.C = c->d_probs;  g.epi = 1; }
     g.ldc = c->ldw[l + 1];
     if (l == c->L && train_labels) {
       g.epi = 4;
       g.labels = train_labels; g.dz = c->d_dz[c->L]; g.lddz = c->ldw[c->L + 1]; g.stats = c->d_stats;
-      g.db = c->d_grads + Bt(c, c->L).off;
-      g.bk = StepBookkeeping{c->d_norm2, (int)c->tensors.size(), c->d_cursor, advance};
+      g.db_slot = 2 * c->L + 2;
+      g.bk = StepBookkeeping{c->d_cursor, advance};
     }
     PB_TRY(gemm(c, g));
     if (l == 0) PB_TRY(issue_prefetch(c));   // no-op unless a pipelined training step armed it
@@ -241,71 +275,26 @@ int forward_logits(pycnn_b200_ctx* c, const float* x, int bs, const int32_t* tra
 }
 
 // logits live in c->d_probs.  train: writes dZ, accumulates loss/#correct and db_o, does the step bookkeeping.
-// ---- fused MLP tail (mlp_tail.cuh): layer-1 fix-up + layers 2..L+1 + softmax/CE/dZ in one launch --------------
-bool tail_supported(const pycnn_b200_ctx* c) {
-  if (c->math_mode != PYCNN_B200_MATH_TF32 || !c->use_tail || c->L < 1 || c->L > tail::MAX_TAIL) return false;
-  if (c->C > tail::MAX_C) return false;
-  if (c->dims[1] > tail::MAX_W) return false;
-  for (int l = 2; l <= c->L; ++l)
-    if (c->dims[l] > tail::MAX_N) return false;
-  return true;
-}
-
-// z1 (raw layer-1 accumulations, no bias) is in d_act[0]; leaves a1..aL in d_act, dZ_out in d_dz[L], loss/#correct
-// in d_stats and db_o in the gradient buffer (which must already be zero)
-int tail_forward_train(pycnn_b200_ctx* c, int bs, const int32_t* labels, int64_t advance) {
-  tail::TailArgs t{};
-  t.bs = bs; t.nl = c->L;                      // tail layers = hidden layers 2..L plus the output layer
-  CUtensorMap maps[1 + tail::MAX_TAIL];
-  PB_TRY(make_map_kmajor(c, &maps[0], c->d_act[0], bs, c->dims[1], c->ldw[1], 128));
-  for (int j = 0; j < t.nl; ++j) {
-    const int l = j + 1;                       // network layer index of tail layer j
-    t.K[j] = (int)c->dims[l]; t.N[j] = (int)c->dims[l + 1];
-    t.bias[j] = c->d_params + c->tensors[2 * l + 1].off;
-    t.act_out[j] = (l < c->L) ? c->d_act[l] : nullptr;
-    t.ld_out[j] = c->ldw[l + 1];
-    const TensorDesc& w = c->tensors[2 * l];
-    PB_TRY(make_map_kmajor(c, &maps[1 + j], c->d_params + w.off, w.rows, w.cols, w.ld, (int)round_up(w.rows, 16)));
-  }
-  for (int j = t.nl; j < tail::MAX_TAIL; ++j) maps[1 + j] = maps[1];
-  t.fuse_fixup = 1;
-  t.bias0 = c->d_params + c->tensors[1].off;
-  t.a_in = c->d_act[0]; t.ld_in = c->ldw[1];
-  t.labels = labels;
-  t.dz = c->d_dz[c->L]; t.ld_dz = c->ldw[c->L + 1];
-  t.stats = c->d_stats;
-  t.db_out = c->d_grads + c->tensors[2 * c->L + 1].off;
-  t.bk = StepBookkeeping{c->d_norm2, (int)c->tensors.size(), c->d_cursor, advance};
-  LaunchScope ls(c, KC_GEMM_FWD);
-  const dim3 grid((unsigned)ceil_div(bs, 128)), block(tail::THREADS);
-  const size_t smem = (size_t)tail::SMEM_BYTES;
-  const int64_t cpad = c->ldw[c->L + 1];        // pad4(C): the dZ row pitch must fit in the register tile too
-  if (cpad <= 16)
-    PB_CUDA(launch_pdl(c, tail::mlp_tail_forward_kernel<16>, grid, block, smem, c->stream, maps[0], maps[1], maps[2], maps[3], maps[4], t));
-  else if (cpad <= 32)
-    PB_CUDA(launch_pdl(c, tail::mlp_tail_forward_kernel<32>, grid, block, smem, c->stream, maps[0], maps[1], maps[2], maps[3], maps[4], t));
-  else
-    PB_CUDA(launch_pdl(c, tail::mlp_tail_forward_kernel<64>, grid, block, smem, c->stream, maps[0], maps[1], maps[2], maps[3], maps[4], t));
-  return 0;
-}
-
 int softmax_ce(pycnn_b200_ctx* c, int bs, const int32_t* labels, bool write_probs, bool write_dz, bool write_pred,
                bool stats, bool train = false, int64_t advance = 0) {
   LaunchScope ls(c, KC_SOFTMAX_CE);
-  const int blocks = (int)ceil_div(bs, 8);
-  StepBookkeeping bk{nullptr, 0, nullptr, 0};
-  float* db = nullptr;
+  int blocks = (int)ceil_div(bs, 8);
+  StepBookkeeping bk{nullptr, 0};
+  float* db_part = nullptr;
   size_t smem = 0;
   if (train) {
-    bk.norm2 = c->d_norm2; bk.n_norm = (int)c->tensors.size();
     bk.cursor = c->d_cursor; bk.advance = advance;
-    db = c->d_grads + c->tensors[2 * c->L + 1].off;
-    smem = sizeof(float) * (size_t)c->C;
+    GradPartSlot& gs = c->gp[2 * c->L + 1];            // db_o: one ordered partial per block
+    blocks = std::min(blocks, std::min(gs.cap, 2 * c->num_sms));
+    gs.nparts = blocks;
+    db_part = c->d_gpart + gs.off;
+    smem = sizeof(float) * 8 * (size_t)c->C;
+    PB_CHECK(smem <= 48 * 1024, "too many classes for the softmax kernel's bias-gradient staging (%d)", c->C);
   }
   PB_CUDA(launch_pdl(c, softmax_ce_kernel, dim3(blocks), dim3(256), smem, c->stream, (const float*)c->d_probs, bs, c->C,
                      c->ldw[c->L + 1], labels, write_probs ? c->d_probs : (float*)nullptr,
                      write_dz ? c->d_dz[c->L] : (float*)nullptr, write_pred ? c->d_pred : (int32_t*)nullptr,
-                     write_pred ? c->d_conf : (float*)nullptr, stats ? c->d_stats : (double*)nullptr, db, bk));
+                     write_pred ? c->d_conf : (float*)nullptr, stats ? c->d_stats : (unsigned long long*)nullptr, db_part, bk));
   return 0;
 }
 
@@ -332,7 +321,7 @@ int backward(pycnn_b200_ctx* c, const float* x, int bs) {
       g.B = in; g.ldb = c->ldw[l]; g.b_kmajor = false;
       g.C = c->d_grads + Wt(c, l).off; g.ldc = Wt(c, l).ld;
       g.M = out_n; g.N = in_n; g.K = bs; g.epi = 0; g.cls = (l == 0) ? KC_GEMM_DW1 : KC_GEMM_DW;
-      g.c_is_zero = true;
+      g.grad_slot = 2 * l + 1;
       if (defer && l == 1) {
         deferred = g; have_deferred = true;      // launched below, behind dW of layer 1
       } else if (fork && l > 0) {
@@ -353,7 +342,7 @@ int backward(pycnn_b200_ctx* c, const float* x, int bs) {
       g.C = c->d_dz[l - 1]; g.ldc = c->ldw[l];
       g.M = bs; g.N = in_n; g.K = out_n; g.epi = 3;
       g.mask = c->d_act[l - 1]; g.ldmask = c->ldw[l];
-      g.colsum = c->d_grads + Bt(c, l - 1).off;
+      g.colsum_slot = 2 * (l - 1) + 2;
       g.cls = KC_GEMM_DA;
       PB_TRY(gemm(c, g));
       if (have_deferred && l == 1) PB_CUDA(cudaEventRecord(c->ev_fork[1], main_stream));   // = dW_1's dependency
@@ -384,7 +373,8 @@ int allreduce_grads(pycnn_b200_ctx* c) {
   return 0;
 }
 
-int apply_update(pycnn_b200_ctx* c) {
+// norms_ready: finalize_grads(want_norm) of this step already left the per-chunk sums of squares in d_chunk_norm
+int apply_update(pycnn_b200_ctx* c, bool norms_ready = false) {
   UpdateParams u{};
   u.opt = c->opt; u.rule = c->update_rule;
   u.lr = (float)c->lr; u.beta1 = (float)c->beta1; u.beta2 = (float)c->beta2; u.eps = (float)c->eps;
@@ -400,22 +390,14 @@ int apply_update(pycnn_b200_ctx* c) {
   u.inv_bc1 = (float)(1.0 / bc1); u.inv_bc2 = (float)(1.0 / bc2);
   u.beta1_d = c->beta1; u.beta2_d = c->beta2;
   u.steps_done = c->d_cursor;   // CuPy rule: bias corrections from the device-side step count (graph-replayable)
-  // small networks: norm + clip + update in one launch with a grid barrier (all chunk blocks co-resident:
-  // <= 4 blocks per SM asked of a kernel that fits 8)
-  if (c->update_rule == PYCNN_B200_RULE_CPU && c->fuse_update && c->num_chunks <= c->update_blocks_per_sm * c->num_sms) {
-    LaunchScope ls(c, KC_UPDATE);
-    PB_CUDA(launch_pdl(c, norm_clip_update_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, c->d_params,
-                       (const float*)c->d_grads, c->d_m, c->d_v, (const Chunk*)c->d_chunks, c->d_norm2, u, c->d_update_bar));
-    return 0;
-  }
-  if (c->update_rule == PYCNN_B200_RULE_CPU) {   // d_norm2 was zeroed by this step's softmax kernel
+  if (c->update_rule == PYCNN_B200_RULE_CPU && !norms_ready) {   // clip norms of a gradient that is complete in d_grads
     LaunchScope ls(c, KC_SQNORM);
     PB_CUDA(launch_pdl(c, grad_sqnorm_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, (const float*)c->d_grads,
-                       (const Chunk*)c->d_chunks, c->d_norm2, trace_slot(c, KC_SQNORM)));
+                       (const Chunk*)c->d_chunks, c->d_chunk_norm, trace_slot(c, KC_SQNORM)));
   }
   LaunchScope ls(c, KC_UPDATE);
   PB_CUDA(launch_pdl(c, clip_update_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, c->d_params,
-                     (const float*)c->d_grads, c->d_m, c->d_v, (const Chunk*)c->d_chunks, (const double*)c->d_norm2, u,
+                     (const float*)c->d_grads, c->d_m, c->d_v, (const Chunk*)c->d_chunks, (const double*)c->d_chunk_norm, u,
                      trace_slot(c, KC_UPDATE)));
   return 0;
 }
@@ -448,21 +430,11 @@ int p2p_exchange_update(pycnn_b200_ctx* c) {
   }
   t.rank = c->rank; t.world = c->world; t.chunk0 = c->p2p_chunk0; t.nchunks = c->p2p_nchunks;
   const int grid = std::max(1, c->p2p_nchunks);
-  // every rank must take the same branch: the decision depends only on the (identical) network and world size
-  const int max_owned = (int)ceil_div(c->num_chunks, c->world);
-  if (c->p2p_fused && max_owned <= 2 * c->num_sms) {     // whole grid co-resident even beside the prefetch gather
-    UpdateParams u = make_update_params(c);
-    LaunchScope ls(c, KC_ALLREDUCE);
-    PB_CUDA(launch_pdl(c, p2p::p2p_fused_kernel, dim3(grid), dim3(256), 0, c->stream, t, (const Chunk*)c->d_chunks,
-                       c->d_p2p_seq, c->d_norm_part, (int)c->tensors.size(), c->d_m, c->d_v, u, c->d_blocks_done,
-                       trace_slot(c, KC_ALLREDUCE)));
-    return 0;
-  }
   {
     LaunchScope ls(c, KC_ALLREDUCE);
     PB_CUDA(launch_pdl(c, p2p::p2p_reduce_kernel, dim3(grid), dim3(256), 0, c->stream, t, (const Chunk*)c->d_chunks,
-                       (const long long*)c->d_p2p_seq, c->d_norm_part, (int)c->tensors.size(), c->d_blocks_done,
-                       trace_slot(c, KC_ALLREDUCE)));
+                       (const long long*)c->d_p2p_seq, c->d_chunk_norm, (const int2*)c->d_tensor_chunks, (int)c->tensors.size(),
+                       c->d_blocks_done, trace_slot(c, KC_ALLREDUCE)));
   }
   UpdateParams u = make_update_params(c);
   LaunchScope ls(c, KC_UPDATE);
@@ -512,43 +484,34 @@ int join_prefetch(pycnn_b200_ctx* c) {
 
 // full step on x [bs, Dp] + labels (device).  bs may be 0 on a rank whose slice is empty.
 int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int bs, bool update, int64_t advance = 0) {
+  begin_grads(c);
   if (bs > 0) {
-    PB_TRY(zero_grads(c, true));
-    if (tail_supported(c)) {
-      // layer 1 as a raw (bias-free) GEMM, everything after it in one fused kernel
-      GemmCall g{};
-      g.A = x; g.lda = c->ldw[0]; g.a_kmajor = true;
-      g.B = c->d_params + Wt(c, 0).off; g.ldb = Wt(c, 0).ld; g.b_kmajor = true;
-      g.C = c->d_act[0]; g.ldc = c->ldw[1];
-      g.M = bs; g.N = (int)c->dims[1]; g.K = (int)c->dims[0]; g.epi = 0; g.cls = KC_GEMM_FWD1;
-      PB_TRY(gemm(c, g));
-      PB_TRY(issue_prefetch(c));
-      PB_TRY(join_zero_grads(c));
-      PB_TRY(tail_forward_train(c, bs, labels, advance));
+    if (softmax_fusable(c)) {
+      PB_TRY(forward_logits(c, x, bs, labels, advance));
     } else {
-      if (softmax_fusable(c)) {
-        PB_TRY(forward_logits(c, x, bs, labels, advance));
-      } else {
-        PB_TRY(forward_logits(c, x, bs));
-        // probs are not written during training; dZ goes to its own buffer
-        PB_TRY(softmax_ce(c, bs, labels, false, true, false, true, true, advance));
-      }
+      PB_TRY(forward_logits(c, x, bs));
+      // probs are not written during training; dZ goes to its own buffer
+      PB_TRY(softmax_ce(c, bs, labels, false, true, false, true, true, advance));
     }
     PB_TRY(backward(c, x, bs));
   } else {   // empty shard on this rank: contribute zero gradients, still advance the cursor
     PB_TRY(zero_grads(c));
     LaunchScope ls(c, KC_MISC);
-    StepBookkeeping bk{c->d_norm2, (int)c->tensors.size(), c->d_cursor, advance};
-    step_bookkeeping_kernel<<<1, 256, 0, c->stream>>>(bk);
+    StepBookkeeping bk{c->d_cursor, advance};
+    step_bookkeeping_kernel<<<1, 32, 0, c->stream>>>(bk);
     PB_CUDA(cudaGetLastError());
     PB_TRY(issue_prefetch(c));
   }
+  // single GPU: the clip norms come out of the same pass that adds the partial sums; with an exchange they must be
+  // those of the REDUCED gradient and are taken after it
+  const bool local_norms = update && c->world <= 1 && c->update_rule == PYCNN_B200_RULE_CPU;
+  PB_TRY(finalize_grads(c, local_norms));
   if (update) {
     if (c->p2p) {
       PB_TRY(p2p_exchange_update(c));
     } else {
       PB_TRY(allreduce_grads(c));
-      PB_TRY(apply_update(c));
+      PB_TRY(apply_update(c, local_norms));
     }
   }
   return 0;
@@ -652,19 +615,24 @@ int reset_cursor(pycnn_b200_ctx* c) {
 }
 
 int zero_stats(pycnn_b200_ctx* c) {
-  PB_CUDA(cudaMemsetAsync(c->d_stats, 0, 2 * sizeof(double), c->stream));
+  PB_CUDA(cudaMemsetAsync(c->d_stats, 0, kStatsWords * sizeof(unsigned long long), c->stream));
   return 0;
+}
+
+// fixed-point loss total -> double (NaN when any contribution was non-finite, as the reference's float sum would be)
+double stats_loss(const unsigned long long* w) {
+  return w[2] ? std::nan("") : (double)(long long)w[0] / kLossFixedScale;
 }
 
 int read_stats(pycnn_b200_ctx* c, double* loss_sum, int64_t* correct, bool allreduce) {
   if (allreduce && c->world > 1 && c->nccl_comm) {
     NcclApi* api = nccl_api();
-    PB_NCCL(api, api->AllReduce(c->d_stats, c->d_stats, 2, kNcclFloat64, kNcclSum, c->nccl_comm, c->stream));
+    PB_NCCL(api, api->AllReduce(c->d_stats, c->d_stats, kStatsWords, kNcclInt64, kNcclSum, c->nccl_comm, c->stream));
   }
-  PB_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PB_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, kStatsWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   PB_CUDA(cudaStreamSynchronize(c->stream));
-  if (loss_sum) *loss_sum = c->h_stats[0];
-  if (correct) *correct = (int64_t)llround(c->h_stats[1]);
+  if (loss_sum) *loss_sum = stats_loss(c->h_stats);
+  if (correct) *correct = (int64_t)c->h_stats[1];
   return 0;
 }
 
@@ -707,7 +675,6 @@ void p2p_detach(pycnn_b200_ctx* c) {
       c->p2p_peer_ptrs[k][r] = nullptr;
     }
   free_dev(c->p2p_sync); c->p2p_sync = nullptr;
-  free_dev(c->d_norm_part); c->d_norm_part = nullptr;
   free_dev(c->d_p2p_seq); c->d_p2p_seq = nullptr;
   free_dev(c->d_blocks_done); c->d_blocks_done = nullptr;
   c->p2p = false;
@@ -717,9 +684,9 @@ void free_network(pycnn_b200_ctx* c) {
   p2p_detach(c);
   free_workspace(c);
   free_dev(c->d_params); free_dev(c->d_grads); free_dev(c->d_m); free_dev(c->d_v);
-  free_dev(c->d_chunks); free_dev(c->d_norm2);
+  free_dev(c->d_chunks); free_dev(c->d_chunk_norm); free_dev(c->d_tensor_chunks); c->d_tensor_chunks = nullptr;
   c->d_params = c->d_grads = c->d_m = c->d_v = nullptr;
-  c->d_chunks = nullptr; c->d_norm2 = nullptr;
+  c->d_chunks = nullptr; c->d_chunk_norm = nullptr;
   c->tensors.clear(); c->dims.clear(); c->ldw.clear();
   c->P = 0;
 }
@@ -785,15 +752,12 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_pf_join, cudaEventDisableTiming));
   for (auto& ev : c->ev_fork) CREATE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-  CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_zero, cudaEventDisableTiming));
   for (auto& ev : c->events) CREATE_CUDA(cudaEventCreate(&ev));
   CREATE_CUDA(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming));
-  CREATE_CUDA(cudaMalloc(&c->d_stats, 2 * sizeof(double)));
-  CREATE_CUDA(cudaMemset(c->d_stats, 0, 2 * sizeof(double)));
-  CREATE_CUDA(cudaMallocHost(&c->h_stats, 2 * sizeof(double)));
-  CREATE_CUDA(cudaMalloc(&c->d_update_bar, 2 * sizeof(unsigned long long)));
-  CREATE_CUDA(cudaMemset(c->d_update_bar, 0, 2 * sizeof(unsigned long long)));
+  CREATE_CUDA(cudaMalloc(&c->d_stats, kStatsWords * sizeof(unsigned long long)));
+  CREATE_CUDA(cudaMemset(c->d_stats, 0, kStatsWords * sizeof(unsigned long long)));
+  CREATE_CUDA(cudaMallocHost(&c->h_stats, kStatsWords * sizeof(unsigned long long)));
   CREATE_CUDA(cudaMalloc(&c->d_cursor, 2 * sizeof(int64_t)));
   CREATE_CUDA(cudaMemset(c->d_cursor, 0, 2 * sizeof(int64_t)));
 #undef CREATE_CUDA
@@ -802,25 +766,14 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_FORK"); if (g && g[0] == '0') { cudaStreamDestroy(c->side_stream); c->side_stream = nullptr; } }
   { const char* g = getenv("PYCNN_B200_CARVEOUT"); if (g && g[0] == '0') c->uniform_carveout = false; }
   { const char* g = getenv("PYCNN_B200_FORCE_BN"); if (g && (atoi(g) == 64 || atoi(g) == 128 || atoi(g) == 256)) c->force_bn = atoi(g); }
-  { const char* g = getenv("PYCNN_B200_P2P_FUSED"); if (g) c->p2p_fused = (g[0] == '1'); }
   { const char* g = getenv("PYCNN_B200_DEFER_DW"); if (g && g[0] == '0') c->defer_last_dw = false; }
   { const char* g = getenv("PYCNN_B200_GRAPH_STEPS"); if (g && atoi(g) > 0) c->graph_steps = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PF_CTAS"); if (g && atoi(g) > 0) c->pf_ctas_per_sm = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PREFETCH"); if (g && g[0] == '0') c->use_prefetch = false; }
-  { const char* g = getenv("PYCNN_B200_FUSE_UPDATE"); if (g) c->fuse_update = (g[0] == '1'); }
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->update_blocks_per_sm, norm_clip_update_kernel, 256, 0) != cudaSuccess) {
-    c->update_blocks_per_sm = 0; (void)cudaGetLastError();
-  }
-  c->update_blocks_per_sm = std::min(c->update_blocks_per_sm, 4);   // leave room for whatever else is resident
   { const char* g = getenv("PYCNN_B200_FUSE_SOFTMAX"); if (g && g[0] == '0') c->fuse_softmax = false; }
   { const char* g = getenv("PYCNN_B200_ONE_WAVE"); if (g && g[0] == '0') c->one_wave_tiles = false; }
   { const char* g = getenv("PYCNN_B200_PAIR"); if (g && g[0] == '0') c->use_pair = false; }
   { const char* g = getenv("PYCNN_B200_CLUSTER_SPLITK"); if (g && g[0] == '0') c->use_cluster_splitk = false; }
-  { const char* g = getenv("PYCNN_B200_FUSED_TAIL"); if (g) c->use_tail = (g[0] == '1'); }
-  { cudaError_t e = cudaFuncSetAttribute(tail::mlp_tail_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail::mlp_tail_forward_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail::mlp_tail_forward_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
-    if (e != cudaSuccess) { fail("cudaFuncSetAttribute(mlp_tail) failed: %s", cudaGetErrorString(e)); return bail(1); } }
   if (c->uniform_carveout) {
     // same shared-memory carve-out as the GEMM kernels (see prepare_tc_gemm) for everything that runs beside them
     cudaError_t e = cudaSuccess;
@@ -828,9 +781,8 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     };
     prefer((const void*)gather_rows_kernel); prefer((const void*)softmax_ce_kernel); prefer((const void*)grad_sqnorm_kernel);
-    prefer((const void*)clip_update_kernel); prefer((const void*)norm_clip_update_kernel); prefer((const void*)gemm_fixup_kernel); prefer((const void*)step_bookkeeping_kernel);
+    prefer((const void*)clip_update_kernel); prefer((const void*)splitk_reduce_kernel); prefer((const void*)grad_finalize_kernel); prefer((const void*)step_bookkeeping_kernel);
     prefer((const void*)colsum_kernel); prefer((const void*)p2p::p2p_reduce_kernel); prefer((const void*)p2p::p2p_update_kernel);
-    prefer((const void*)p2p::p2p_fused_kernel);
     if (e != cudaSuccess) { fail("cudaFuncSetAttribute(carve-out) failed: %s", cudaGetErrorString(e)); return bail(1); }
   }
   if (tc_gemm_prepare(c) != 0 || tc_extract_prepare(c) != 0) return bail(1);
@@ -846,7 +798,6 @@ int pycnn_b200_destroy(pycnn_b200_ctx* c) {
   drop_graphs(c);
   pycnn_b200_comm_destroy(c);
   free_dev(c->d_cursor);
-  free_dev(c->d_update_bar);
   free_dev(c->d_trace);
   free_network(c);
   free_dataset(c);
@@ -875,7 +826,6 @@ int pycnn_b200_destroy(pycnn_b200_ctx* c) {
   if (c->ev_pf_join) cudaEventDestroy(c->ev_pf_join);
   for (auto& ev : c->ev_fork) if (ev) cudaEventDestroy(ev);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
-  if (c->ev_zero) cudaEventDestroy(c->ev_zero);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -1052,6 +1002,7 @@ int pycnn_b200_cross_entropy(pycnn_b200_ctx* c, const double* preds, const doubl
 int pycnn_b200_set_network(pycnn_b200_ctx* c, int64_t D, const int* layers, int L, int C) {
   CTX_GUARD(c);
   PB_CHECK(D > 0 && L >= 0 && C > 0 && (L == 0 || layers), "bad network shape");
+  PB_CHECK(2 * (L + 1) <= GradParts::MAX_T, "pycnn_b200 supports at most %d hidden layers (got %d)", GradParts::MAX_T / 2 - 1, L);
   for (int l = 0; l < L; ++l) PB_CHECK(layers[l] > 0, "layer %d has size %d", l, layers[l]);
   PB_CUDA(cudaStreamSynchronize(c->stream));
   drop_graphs(c);
@@ -1080,13 +1031,20 @@ int pycnn_b200_set_network(pycnn_b200_ctx* c, int64_t D, const int* layers, int 
   const int64_t kChunk = 2048;   // one 256-thread block per chunk: >= 4 waves of blocks at 1.1 M parameters
   for (size_t t = 0; t < c->tensors.size(); ++t) {
     const int64_t len = c->tensors[t].rows * c->tensors[t].ld;
-    for (int64_t o = 0; o < len; o += kChunk) chunks.push_back({(int)t, 0, c->tensors[t].off + o, std::min(kChunk, len - o)});
+    const int first = (int)chunks.size(), count = (int)ceil_div(len, kChunk);
+    for (int64_t o = 0; o < len; o += kChunk)
+      chunks.push_back({(int)t, first, count, 0, c->tensors[t].off + o, std::min(kChunk, len - o), o});
   }
   c->num_chunks = (int)chunks.size();
   PB_CUDA(cudaMalloc(&c->d_chunks, sizeof(Chunk) * chunks.size()));
   PB_CUDA(cudaMemcpy(c->d_chunks, chunks.data(), sizeof(Chunk) * chunks.size(), cudaMemcpyHostToDevice));
-  PB_CUDA(cudaMalloc(&c->d_norm2, sizeof(double) * c->tensors.size()));
-  PB_CUDA(cudaMemset(c->d_norm2, 0, sizeof(double) * c->tensors.size()));
+  std::vector<int2> tchunks(c->tensors.size());
+  for (const Chunk& ch : chunks) tchunks[ch.tensor] = make_int2(ch.first_chunk, ch.n_chunks);
+  PB_CUDA(cudaMalloc(&c->d_tensor_chunks, sizeof(int2) * tchunks.size()));
+  PB_CUDA(cudaMemcpy(c->d_tensor_chunks, tchunks.data(), sizeof(int2) * tchunks.size(), cudaMemcpyHostToDevice));
+  c->h_chunks = chunks;
+  PB_CUDA(cudaMalloc(&c->d_chunk_norm, sizeof(double) * chunks.size()));
+  PB_CUDA(cudaMemset(c->d_chunk_norm, 0, sizeof(double) * chunks.size()));
   c->t = 0;
   return 0;
 }
@@ -1398,26 +1356,28 @@ static bool host_ptr_is_device_visible(const void* p) {
   return at.type == cudaMemoryTypeHost && at.devicePointer != nullptr;
 }
 
-int pycnn_b200_train_epoch_images(pycnn_b200_ctx* c, const uint8_t* images, const int32_t* labels, const int64_t* perm,
-                                  int64_t n, int S, int batch_size, double* step_stats, double* loss_sum,
-                                  int64_t* correct) {
+int pycnn_b200_train_epoch_images(pycnn_b200_ctx* c, const uint8_t* images, const int32_t* labels, int64_t num_images,
+                                  const int64_t* perm, int64_t n, int S, int batch_size, double* step_stats,
+                                  double* loss_sum, int64_t* correct) {
   CTX_GUARD(c);
   PB_CHECK(c->d_params, "set_network must be called first");
   PB_CHECK(n > 0 && batch_size > 0 && images && labels, "empty epoch");
   PB_CHECK(feature_count(c, S) == c->D, "image_size %d with %d filters gives %lld features, network expects %lld", S, c->F, (long long)feature_count(c, S), (long long)c->D);
+  PB_CHECK(num_images > 0 && (perm || n <= num_images), "epoch of %lld rows over %lld images", (long long)n, (long long)num_images);
   if (perm)
-    for (int64_t i = 0; i < n; ++i) PB_CHECK(perm[i] >= 0, "negative row index at %lld", (long long)i);
+    for (int64_t i = 0; i < n; ++i)
+      PB_CHECK(perm[i] >= 0 && perm[i] < num_images, "row index %lld at position %lld out of range [0,%lld)", (long long)perm[i], (long long)i, (long long)num_images);
   const int W = c->world, R = c->rank;
   const int64_t img_bytes = (int64_t)S * S * 3;
   const int64_t per_rank_max = ceil_div(std::min<int64_t>(batch_size, n), W);
   const int64_t num_steps = ceil_div(n, batch_size);
   PB_TRY(ensure_workspace(c, per_rank_max));
   PB_TRY(ensure_stream_slots(c, per_rank_max * img_bytes, per_rank_max));
-  if ((size_t)(2 * num_steps) > c->step_stats_cap) {
+  if ((size_t)(kStatsWords * num_steps) > c->step_stats_cap) {
     if (c->h_step_stats) PB_CUDA(cudaFreeHost(c->h_step_stats));
     c->h_step_stats = nullptr;
-    c->step_stats_cap = (size_t)round_up(2 * num_steps, 1024);
-    PB_CUDA(cudaMallocHost(&c->h_step_stats, sizeof(double) * c->step_stats_cap));
+    c->step_stats_cap = (size_t)round_up(kStatsWords * num_steps, 1024);
+    PB_CUDA(cudaMallocHost(&c->h_step_stats, sizeof(unsigned long long) * c->step_stats_cap));
   }
   const bool zero_copy = perm && host_ptr_is_device_visible(images) && host_ptr_is_device_visible(labels);
   const bool bounce = perm && !zero_copy;
@@ -1481,11 +1441,15 @@ int pycnn_b200_train_epoch_images(pycnn_b200_ctx* c, const uint8_t* images, cons
       return 0;
     }));
     if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += 1;
-    PB_CUDA(cudaMemcpyAsync(c->h_step_stats + 2 * step, c->d_stats, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PB_CUDA(cudaMemcpyAsync(c->h_step_stats + kStatsWords * step, c->d_stats, kStatsWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     PB_CUDA(cudaEventRecord(c->ev_compute[slot], c->stream));
   }
   PB_TRY(read_stats(c, loss_sum, correct, true));
-  if (step_stats) memcpy(step_stats, c->h_step_stats, sizeof(double) * 2 * (size_t)num_steps);
+  if (step_stats)
+    for (int64_t i = 0; i < num_steps; ++i) {
+      step_stats[2 * i] = stats_loss(c->h_step_stats + kStatsWords * i);
+      step_stats[2 * i + 1] = (double)c->h_step_stats[kStatsWords * i + 1];
+    }
   return 0;
 }
 
@@ -1649,11 +1613,12 @@ int pycnn_b200_backward_last(pycnn_b200_ctx* c, const int32_t* labels, int bs) {
   PB_CUDA(cudaMemcpyAsync(c->d_blabels, labels, sizeof(int32_t) * bs, cudaMemcpyHostToDevice, c->stream));
   // d_probs holds probabilities after forward_features; softmax is idempotent on logits only, so redo the
   // forward to regenerate logits from the activations' inputs (cheap at the sizes this compat path sees)
+  begin_grads(c);
   PB_TRY(forward_logits(c, c->d_x, bs));
   PB_TRY(zero_stats(c));
-  PB_TRY(zero_grads(c));
   PB_TRY(softmax_ce(c, bs, c->d_blabels, false, true, false, true, true, 0));
   PB_TRY(backward(c, c->d_x, bs));
+  PB_TRY(finalize_grads(c, false));
   PB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -1712,8 +1677,6 @@ int pycnn_b200_comm_ipc_export(pycnn_b200_ctx* c, char* blob) {
   // fresh sync state: zeroed BEFORE the handles travel, so no peer can write into it earlier
   PB_CUDA(cudaMalloc(&c->p2p_sync, sizeof(p2p::SyncBlock)));
   PB_CUDA(cudaMemset(c->p2p_sync, 0, sizeof(p2p::SyncBlock)));
-  PB_CUDA(cudaMalloc(&c->d_norm_part, sizeof(double) * p2p::MAX_TENSORS));
-  PB_CUDA(cudaMemset(c->d_norm_part, 0, sizeof(double) * p2p::MAX_TENSORS));
   PB_CUDA(cudaMalloc(&c->d_p2p_seq, 2 * sizeof(long long)));
   PB_CUDA(cudaMalloc(&c->d_blocks_done, 2 * sizeof(unsigned int)));
   PB_CUDA(cudaMemset(c->d_blocks_done, 0, 2 * sizeof(unsigned int)));
@@ -1757,8 +1720,33 @@ int pycnn_b200_comm_ipc_attach(pycnn_b200_ctx* c, const char* blobs, int rank, i
   return 0;
 }
 
+// Collective (every rank): make Adam's m, v complete on every rank.  In the peer-memory mode a rank only updates the
+// state of the chunks it owns; the shards are disjoint, so zero-fill + own range + all-reduce(sum) assembles them.
+// The flat gradient buffer is dead between steps and serves as the scratch.
+int pycnn_b200_comm_sync_opt_state(pycnn_b200_ctx* c) {
+  CTX_GUARD(c);
+  if (!c->p2p || c->world <= 1 || !c->d_m) return 0;
+  NcclApi* api = nccl_api();
+  PB_CHECK(api && c->nccl_comm, "the peer-memory mode needs the NCCL communicator to gather optimizer state");
+  int64_t lo = 0, hi = 0;
+  if (c->p2p_nchunks > 0) {
+    lo = c->h_chunks[c->p2p_chunk0].off;
+    const Chunk& last = c->h_chunks[c->p2p_chunk0 + c->p2p_nchunks - 1];
+    hi = last.off + last.len;
+  }
+  const int blocks = grid_for(c->P, 256, c->num_sms);
+  for (float* state : {c->d_m, c->d_v}) {
+    p2p::owned_range_kernel<<<blocks, 256, 0, c->stream>>>(state, c->d_grads, c->P, lo, hi);
+    PB_CUDA(cudaGetLastError());
+    PB_NCCL(api, api->AllReduce(c->d_grads, state, (size_t)c->P, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream));
+  }
+  PB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int pycnn_b200_comm_ipc_detach(pycnn_b200_ctx* c) {
   CTX_GUARD(c);
+  PB_TRY(pycnn_b200_comm_sync_opt_state(c));   // the replicated update that takes over needs the whole state everywhere
   drop_graphs(c);
   p2p_detach(c);
   return 0;

@@ -14,7 +14,7 @@ struct NcclUniqueId {
   char internal[128];
 };
 typedef void* NcclComm;
-enum { kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0 };
+enum { kNcclInt64 = 4, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0 };
 
 struct NcclApi {
   void* handle = nullptr;

@@ -89,11 +89,21 @@ struct TensorDesc {
   int64_t ld;    // row pitch in floats (multiple of 4)
 };
 
-struct Chunk {  // unit of work for sqnorm/update kernels
+struct Chunk {  // unit of work for the finalize / norm / update kernels: <= 2048 floats of one tensor
   int tensor;
+  int first_chunk;   // index of the tensor's first chunk and how many chunks it has (per-tensor norm = ordered sum of
+  int n_chunks;      // the chunk norms)
   int pad;
-  int64_t off;
+  int64_t off;       // offset in the flat buffers
   int64_t len;
+  int64_t rel;       // offset inside the tensor (off - tensor.off)
+};
+
+struct GradPartSlot {   // one gradient tensor's region of the ordered-partial-sum arena (elementwise.cuh: GradParts)
+  int64_t off = 0;      // floats from d_gpart
+  int64_t stride = 0;   // distance between consecutive partials (the tensor's padded length)
+  int cap = 0;          // partials the region can hold
+  int nparts = 0;       // partials the current step's producer wrote (0: it wrote the flat gradient buffer directly)
 };
 
 struct NcclApi;  // comm.cuh
@@ -108,8 +118,7 @@ struct pycnn_b200_ctx {
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // H2D staging for streamed batches
   cudaStream_t side_stream = nullptr;  // backward: the shallow dW GEMMs run beside the dA chain (fork/join inside the graph)
-  cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_zero = nullptr;
-  bool zero_pending = false;           // this step's gradient memset is in flight on side_stream (join_zero_grads)
+  cudaEvent_t ev_fork[8] = {}, ev_join = nullptr;
   cudaStream_t pf_stream = nullptr;    // gather of the NEXT step's rows, overlapped with this step's backward pass
   cudaEvent_t ev_pf_fork = nullptr, ev_pf_join = nullptr;
   struct Prefetch {                    // armed by graphed_step_rows_pf, consumed by step_on_batch
@@ -125,7 +134,6 @@ struct pycnn_b200_ctx {
   unsigned long long* d_trace = nullptr;
   int trace_cap = 0, trace_next = 0;
   std::vector<int> trace_cls;          // kernel class of each slot, + 100 x stream id (0 main, 1 side, 2 prefetch)
-  bool p2p_fused = false;              // reduce-scatter + norms + update + all-gather in ONE launch (PYCNN_B200_P2P_FUSED=1)
   int force_bn = 0;                    // PYCNN_B200_FORCE_BN: tile width override for deep-K GEMMs (experiments)
   int last_gemm_ctas = 0;              // grid size of the most recent tensor-core GEMM launch
   bool defer_last_dw = true;           // backward: dW of layer 2 runs on the SMs dW of layer 1 leaves idle (PYCNN_B200_DEFER_DW=0)
@@ -133,9 +141,6 @@ struct pycnn_b200_ctx {
   int graph_steps = 16;                // max training steps per captured graph: a graph launch costs ~15 us of idle GPU (PYCNN_B200_GRAPH_STEPS)
   int pf_ctas_per_sm = 2;              // gather CTAs per SM on the prefetch stream (PYCNN_B200_PF_CTAS)
   bool uniform_carveout = true;        // elementwise kernels ask for the GEMMs' L1/shared split (PYCNN_B200_CARVEOUT=0 disables)
-  bool fuse_update = false;            // norm + clip + update in one launch with a grid barrier (PYCNN_B200_FUSE_UPDATE=1; measured: no gain over two PDL-chained launches)
-  unsigned long long* d_update_bar = nullptr;
-  int update_blocks_per_sm = 0;        // co-resident blocks of norm_clip_update_kernel (grid-barrier safety bound)
   bool fuse_softmax = true;            // training: softmax/CE/dZ in the output-layer GEMM's epilogue (PYCNN_B200_FUSE_SOFTMAX=0: own kernel)
   bool one_wave_tiles = true;          // shallow-K GEMMs: widen the tile rather than run a second wave (PYCNN_B200_ONE_WAVE=0 disables)
   bool use_pair = true;                // M-adjacent GEMM CTAs share the B tile by TMA multicast (PYCNN_B200_PAIR=0 disables)
@@ -164,7 +169,12 @@ struct pycnn_b200_ctx {
   float *d_params = nullptr, *d_grads = nullptr, *d_m = nullptr, *d_v = nullptr;
   pb::Chunk* d_chunks = nullptr;
   int num_chunks = 0;
-  double* d_norm2 = nullptr;
+  std::vector<pb::Chunk> h_chunks;      // host copy of the chunk table
+  int2* d_tensor_chunks = nullptr;      // per tensor: (first chunk, chunk count)
+  double* d_chunk_norm = nullptr;       // [num_chunks] sum of squares of each chunk of the (reduced) gradient
+  float* d_gpart = nullptr;             // ordered-partial-sum arena (sized by ensure_workspace for the batch capacity)
+  int64_t gpart_floats = 0;
+  pb::GradPartSlot gp[64];              // per tensor
 
   // optimizer
   int opt = PYCNN_B200_OPT_SGD;
@@ -192,9 +202,9 @@ struct pycnn_b200_ctx {
   float* d_gemm_ws = nullptr;         // split-K workspace
   size_t gemm_ws_bytes = 0;
 
-  // stats accumulators: [0] loss (double), [1] correct (as unsigned long long bits)
-  double* d_stats = nullptr;
-  double* h_stats = nullptr;  // pinned
+  // stats accumulators (elementwise.cuh: stats_add): [0] loss sum in 2^-32 fixed point, [1] #correct, [2] non-finite count
+  unsigned long long* d_stats = nullptr;
+  unsigned long long* h_stats = nullptr;  // pinned
 
   // staging
   uint8_t* d_images = nullptr;
@@ -215,7 +225,7 @@ struct pycnn_b200_ctx {
   cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr};
   uint8_t* h_bounce[2] = {nullptr, nullptr};   // pinned bounce buffers for pageable host memory
   size_t bounce_cap = 0;
-  double* h_step_stats = nullptr;              // pinned ring for per-step (loss, correct) read-backs
+  unsigned long long* h_step_stats = nullptr;  // pinned ring for per-step stats read-backs (kStatsWords words each)
   size_t step_stats_cap = 0;
 
   // comm
@@ -225,7 +235,6 @@ struct pycnn_b200_ctx {
   bool p2p = false;
   void* p2p_sync = nullptr;                 // my SyncBlock (peers write into it)
   void* p2p_peer_ptrs[3][8] = {};           // [grads|params|sync][rank], own entries point at local buffers
-  double* d_norm_part = nullptr;            // per-tensor partial ||g||^2 of my chunk range
   long long* d_p2p_seq = nullptr;           // [0] unused, [1] exchange sequence number (monotonic since attach)
   unsigned int* d_blocks_done = nullptr;
   int p2p_chunk0 = 0, p2p_nchunks = 0;
@@ -249,7 +258,6 @@ struct pycnn_b200_ctx {
   };
   std::map<std::tuple<int, int64_t, int64_t, int64_t, int>, GraphEntry> graphs;
   bool use_graphs = true;
-  bool use_tail = false;         // fused MLP-tail forward kernel (mlp_tail.cuh), opt-in: PYCNN_B200_FUSED_TAIL=1
   bool use_pdl = true;           // programmatic dependent launch between the step's kernels (PYCNN_B200_PDL=0 disables)
   int64_t* d_cursor = nullptr;   // [0] offset into d_idx of the current batch, [1] completed steps (device-side t)
 };

@@ -162,12 +162,27 @@ __global__ void __launch_bounds__(256) gather_host_rows_kernel(const uint8_t* __
 // stats[0] += sum of row losses (double); stats[1] += #correct (as a double, exact below 2^53).
 // Any of probs/dz/pred/conf may be null.  labels may be null (inference: no loss/dz).
 // ---------------------------------------------------------------------------------------------
-struct StepBookkeeping {   // per-step housekeeping folded into the softmax kernel (block 0) to save graph nodes
-  double* norm2;           // per-tensor squared-norm accumulators to zero for this step's grad_sqnorm_kernel
-  int n_norm;
+struct StepBookkeeping {   // per-step housekeeping folded into the softmax kernel / epilogue (block 0) to save graph nodes
   int64_t* cursor;         // cursor[0] += advance (next batch of the permutation); cursor[1] += 1 (step count t)
   int64_t advance;
 };
+__device__ __forceinline__ void step_bookkeeping(const StepBookkeeping& bk) {   // one thread of the launch
+  // advance == 0: the row-gather prefetch branch owns cursor[0] (advance_cursor_kernel on pf_stream); a
+  // read-modify-write of +0 here could swallow its advance
+  if (bk.cursor) { if (bk.advance) bk.cursor[0] += bk.advance; bk.cursor[1] += 1; }
+}
+
+// Running (loss, #correct) totals are integers so that their atomic accumulation is order-independent and a
+// training run reproduces bit for bit: stats[0] = sum of row losses in 2^-32 fixed point (two's complement),
+// stats[1] = #correct, stats[2] = number of non-finite contributions (the host then reports NaN, as the
+// reference's float sum would), stats[3] unused.  |loss sum| < 2^31 covers 10^8 rows at the -log(1e-9) worst case.
+constexpr int kStatsWords = 4;
+constexpr double kLossFixedScale = 4294967296.0;
+__device__ __forceinline__ void stats_add(unsigned long long* stats, double loss, unsigned long long correct) {
+  if (!isfinite(loss)) atomicAdd(&stats[2], 1ull);
+  else atomicAdd(&stats[0], (unsigned long long)__double2ll_rn(loss * kLossFixedScale));
+  if (correct) atomicAdd(&stats[1], correct);
+}
 
 __global__ void advance_cursor_kernel(int64_t* cursor, int64_t advance) {   // tail of the prefetch branch
   if (threadIdx.x == 0) cursor[0] += advance;
@@ -175,33 +190,30 @@ __global__ void advance_cursor_kernel(int64_t* cursor, int64_t advance) {   // t
 
 __global__ void step_bookkeeping_kernel(StepBookkeeping bk) {   // ranks whose shard of a batch is empty
   pdl_wait();
-  if (bk.norm2 && (int)threadIdx.x < bk.n_norm) bk.norm2[threadIdx.x] = 0.0;
-  if (bk.cursor && threadIdx.x == 0) { bk.cursor[0] += bk.advance; bk.cursor[1] += 1; }
+  if (threadIdx.x == 0) step_bookkeeping(bk);
 }
 
+// One warp per row, rows grid-strided (a warp visits its rows in increasing order).  db_part (training): the bias
+// gradient of the output layer as ORDERED partial sums -- block b writes db_part[b * ld + j] = sum over its rows of
+// dZ[., j] (each warp accumulates its own rows in a private smem row, the 8 warp rows are then added in warp order),
+// and grad_finalize_kernel adds the gridDim.x partials in block order: no atomics, bit-reproducible.
 __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict__ logits, int bs, int C,
                                                          int64_t ld, const int32_t* __restrict__ labels,
                                                          float* __restrict__ probs, float* __restrict__ dz,
                                                          int32_t* __restrict__ pred, float* __restrict__ conf,
-                                                         double* __restrict__ stats, float* __restrict__ db,
-                                                         StepBookkeeping bk) {
-  extern __shared__ float s_db[];   // [C] when db != nullptr: block-level bias-gradient partial sums
+                                                         unsigned long long* __restrict__ stats,
+                                                         float* __restrict__ db_part, StepBookkeeping bk) {
+  extern __shared__ float s_db[];   // [8][C] when db_part != nullptr
   pdl_wait();
   pdl_launch_dependents();
   const int warps_per_block = blockDim.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  if (blockIdx.x == 0) {
-    if (bk.norm2 && threadIdx.x < bk.n_norm) bk.norm2[threadIdx.x] = 0.0;
-    if (bk.cursor && threadIdx.x == 0) { bk.cursor[0] += bk.advance; bk.cursor[1] += 1; }
-  }
-  if (db) {
-    for (int j = threadIdx.x; j < C; j += blockDim.x) s_db[j] = 0.f;
-    __syncthreads();
-  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) step_bookkeeping(bk);
+  if (db_part)
+    for (int j = lane; j < C; j += 32) s_db[w * C + j] = 0.f;
   double my_loss = 0.0;
   unsigned long long my_correct = 0ull;
-  if (row < bs) {
+  for (int row = blockIdx.x * warps_per_block + w; row < bs; row += gridDim.x * warps_per_block) {
     const float* z = logits + (int64_t)row * ld;
     float mx = -INFINITY;
     int arg = 0x7fffffff;
@@ -227,45 +239,48 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
       if (probs) probs[(int64_t)row * ld + j] = p;
       const float d = (j < C) ? (p - (j == y ? 1.0f : 0.0f)) : 0.0f;
       if (dz) dz[(int64_t)row * ld + j] = d;
-      if (db && j < C) atomicAdd(&s_db[j], d);           // db_o = sum_rows dZ (backward_pass.pyx:72)
-      if (j == y) my_loss = -log((double)p + 1e-9);
+      if (db_part && j < C) s_db[w * C + j] += d;          // db_o = sum_rows dZ (backward_pass.pyx:72)
+      if (j == y) my_loss += -log((double)p + 1e-9);
     }
     if (lane == 0) {
       if (pred) pred[row] = arg;
       if (conf) conf[row] = inv;  // p[argmax] = exp(0)/s
-      if (y >= 0 && arg == y) my_correct = 1ull;
+      if (y >= 0 && arg == y) my_correct += 1ull;
     }
   }
-  if (db) {
+  if (db_part) {
     __syncthreads();
-    for (int j = threadIdx.x; j < C; j += blockDim.x) atomicAdd(&db[j], s_db[j]);
+    for (int j = threadIdx.x; j < (int)ld; j += blockDim.x) {
+      float t = 0.f;
+      if (j < C)
+        for (int i = 0; i < warps_per_block; ++i) t += s_db[i * C + j];
+      db_part[(int64_t)blockIdx.x * ld + j] = t;
+    }
   }
   if (stats && labels) {
-    // block-level reduction -> one atomic pair per block
+    // block-level reduction (fixed order) -> one integer atomic pair per block
     __shared__ double s_loss[8];
     __shared__ unsigned long long s_corr[8];
     my_loss = warp_sum_d(my_loss);
-    const int w = threadIdx.x >> 5;
     if (lane == 0) { s_loss[w] = my_loss; s_corr[w] = my_correct; }
     __syncthreads();
     if (threadIdx.x == 0) {
       double l = 0.0;
       unsigned long long c = 0ull;
       for (int i = 0; i < warps_per_block; ++i) { l += s_loss[i]; c += s_corr[i]; }
-      atomicAdd(&stats[0], l);
-      atomicAdd(&stats[1], (double)c);   // counts stay exact in a double and reduce with ncclFloat64
+      stats_add(stats, l, c);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6(c): db[n] = sum_rows dZ[m, n]  (backward_pass.pyx:72,93).  dz [bs, ld].  grid (ceil(N/32), R);
-// block (32, 8): thread (x, y) sums rows y, y+8, ... of its row chunk for column x in FP64, the 8 partials
-// are combined through smem and one atomicAdd per (column, chunk) lands in db (zeroed by the caller
-// when R > 1).  Coalesced 128-byte row segments; R is chosen so the grid fills the SMs.
+// K6(c): bias gradients db[n] = sum_rows dZ[m, n]  (backward_pass.pyx:72,93) for the FP32-SIMT path, as ORDERED
+// partial sums: grid (ceil(N/32), R); block (32, 8): thread (x, y) sums rows y, y+8, ... of row chunk blockIdx.y
+// for column x in FP64, the 8 partials are combined through smem in y order and the block writes
+// part[blockIdx.y * ld_part + n]; grad_finalize_kernel adds the R partials in chunk order (no atomics).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dz, int bs, int N, int64_t ld,
-                                                     float* __restrict__ db, int rows_per_block, int accumulate) {
+                                                     float* __restrict__ part, int64_t ld_part, int rows_per_block) {
   __shared__ double red[8][33];
   pdl_wait();
   const int n = blockIdx.x * 32 + threadIdx.x;
@@ -280,41 +295,99 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-    if (gridDim.y == 1 && !accumulate) db[n] = (float)s;
-    else atomicAdd(&db[n], (float)s);
+    part[(int64_t)blockIdx.y * ld_part + n] = (float)s;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K7: per-tensor squared L2 norm of the (all-reduced) gradient, double accumulation.
-// gradient_decent.pyx:33 (np.linalg.norm per tensor).  One block per chunk of the flat buffer.
+// Gradient accumulation is ORDERED, never atomic: a producer that cannot finish a gradient tensor alone (split-K
+// dW GEMMs: one partial per k-slice; bias gradients: one partial per row tile) writes its partial sums side by side
+// into an arena, and grad_finalize_kernel adds them in index order into the flat gradient buffer.  Same inputs ->
+// bit-identical gradients, norms and parameters, run after run (backward_pass.pyx:71-72,92-93 are plain sums).
 // ---------------------------------------------------------------------------------------------
+struct GradParts {               // by-value kernel argument
+  static constexpr int MAX_T = 64;
+  const float* base;             // partial-sum arena
+  int64_t off[MAX_T];            // offset of a tensor's partial 0 in the arena
+  int64_t stride[MAX_T];         // distance between consecutive partials
+  int nparts[MAX_T];             // 0: the producer wrote the flat gradient buffer directly
+};
+
+// fixed-shape block reduction of one double per thread (256 threads): identical result in every thread
+__device__ __forceinline__ double block_sum_d(double v, double* s8) {
+  v = warp_sum_d(v);
+  if ((threadIdx.x & 31) == 0) s8[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += s8[i];
+  __syncthreads();
+  return t;
+}
+
+// One block per chunk of the flat buffer: grads[chunk] = sum_p part[p][chunk] (when the tensor has partials) and,
+// if asked, chunk_norm[chunk] = sum of squares (gradient_decent.pyx:33, np.linalg.norm per tensor -- the per-tensor
+// total is formed by the update kernel from the chunk values in chunk order).
+__global__ void __launch_bounds__(256) grad_finalize_kernel(float* __restrict__ grads, const Chunk* __restrict__ chunks,
+                                                            const GradParts gp, double* __restrict__ chunk_norm,
+                                                            int want_norm, unsigned long long* trace) {
+  __shared__ double s8[8];
+  pdl_wait();
+  pdl_launch_dependents();
+  trace_begin(trace);
+  const Chunk ch = chunks[blockIdx.x];
+  const int np = gp.nparts[ch.tensor];
+  float4* g4 = reinterpret_cast<float4*>(grads + ch.off);
+  const int64_t n4 = ch.len >> 2;  // chunk offsets/lengths are multiples of 4
+  float acc = 0.f;
+  if (np > 0) {
+    const float* p0 = gp.base + gp.off[ch.tensor] + ch.rel;
+    const int64_t stride = gp.stride[ch.tensor];
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p = 0; p < np; p += 8) {      // 8 independent loads in flight, added in index order
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (p + u < np) v[u] = __ldcg(reinterpret_cast<const float4*>(p0 + (int64_t)(p + u) * stride) + i);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (p + u < np) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+      }
+      g4[i] = s;
+      acc = fmaf(s.x, s.x, acc); acc = fmaf(s.y, s.y, acc); acc = fmaf(s.z, s.z, acc); acc = fmaf(s.w, s.w, acc);
+    }
+  } else if (want_norm) {
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = g4[i];
+      acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+    }
+  }
+  if (want_norm) {
+    const double t = block_sum_d((double)acc, s8);
+    if (threadIdx.x == 0) chunk_norm[blockIdx.x] = t;
+  }
+  trace_end(trace);
+}
+
+// norms of a gradient that is already complete in the flat buffer (after an NCCL all-reduce / external exchange)
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restrict__ grads,
                                                           const Chunk* __restrict__ chunks,
-                                                          double* __restrict__ norm2, unsigned long long* trace) {
+                                                          double* __restrict__ chunk_norm, unsigned long long* trace) {
+  __shared__ double s8[8];
   pdl_wait();
   pdl_launch_dependents();
   trace_begin(trace);
   const Chunk ch = chunks[blockIdx.x];
   const float4* g4 = reinterpret_cast<const float4*>(grads + ch.off);
-  const int64_t n4 = ch.len >> 2;  // chunk offsets/lengths are multiples of 4
+  const int64_t n4 = ch.len >> 2;
   float acc = 0.f;
   for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
     const float4 v = g4[i];
-    acc = fmaf(v.x, v.x, acc);
-    acc = fmaf(v.y, v.y, acc);
-    acc = fmaf(v.z, v.z, acc);
-    acc = fmaf(v.w, v.w, acc);
+    acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
   }
-  double d = warp_sum_d((double)acc);
-  __shared__ double s[8];
-  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = d;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s[i];
-    atomicAdd(&norm2[ch.tensor], t);
-  }
+  const double t = block_sum_d((double)acc, s8);
+  if (threadIdx.x == 0) chunk_norm[blockIdx.x] = t;
   trace_end(trace);
 }
 
@@ -326,17 +399,47 @@ struct UpdateParams {
   const int64_t* steps_done;  // device cursor; [1] = Adam step count t of the current step (CuPy rule)
 };
 
+// ||g||^2 of the chunk's tensor: its chunk values added in chunk order by a fixed-shape block reduction, so every
+// block of a tensor (and every run) arrives at the same bits
+__device__ __forceinline__ double tensor_norm2(const double* __restrict__ chunk_norm, const Chunk& ch, double* s8) {
+  double a = 0.0;
+  for (int i = threadIdx.x; i < ch.n_chunks; i += blockDim.x) a += __ldcg(chunk_norm + ch.first_chunk + i);
+  return block_sum_d(a, s8);
+}
 
+__device__ __forceinline__ void adam_or_sgd4(float4& p, float4& mm, float4& vv, const float4& g, float scale,
+                                             const UpdateParams& u, float omb1, float omb2) {
+  float pe[4] = {p.x, p.y, p.z, p.w}, me[4] = {mm.x, mm.y, mm.z, mm.w}, ve[4] = {vv.x, vv.y, vv.z, vv.w};
+  const float ge[4] = {g.x * scale, g.y * scale, g.z * scale, g.w * scale};
+  if (u.opt == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pe[k] -= u.lr * ge[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      me[k] = me[k] * u.beta1 + omb1 * ge[k];
+      ve[k] = ve[k] * u.beta2 + omb2 * (ge[k] * ge[k]);
+      const float mh = me[k] * u.inv_bc1;
+      float vh = ve[k] * u.inv_bc2;
+      if (u.rule == 0) vh = fmaxf(vh, u.eps2);
+      pe[k] -= u.lr * mh / (sqrtf(vh) + u.eps);
+    }
+    mm = make_float4(me[0], me[1], me[2], me[3]);
+    vv = make_float4(ve[0], ve[1], ve[2], ve[3]);
+  }
+  p = make_float4(pe[0], pe[1], pe[2], pe[3]);
+}
 
-// clipped SGD / Adam over the flat buffers; each block handles one chunk and reads its tensor's norm.
+// clipped SGD / Adam over the flat buffers; each block handles one chunk and forms its tensor's norm.
 // CPU rule (gradient_decent.pyx): g *= 5/||g|| when ||g|| > 5 (:33-35); non-finite -> skip tensor
 // (:37-39); Adam m,v in place (:91-95), v_hat floored at eps^2 (:98), w -= lr*m_hat/(sqrt(v_hat)+eps).
 __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ params,
                                                           const float* __restrict__ grads,
                                                           float* __restrict__ m, float* __restrict__ v,
                                                           const Chunk* __restrict__ chunks,
-                                                          const double* __restrict__ norm2, UpdateParams u,
+                                                          const double* __restrict__ chunk_norm, UpdateParams u,
                                                           unsigned long long* trace) {
+  __shared__ double s8[8];
   pdl_wait();
   pdl_launch_dependents();
   trace_begin(trace);
@@ -348,7 +451,7 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ pa
     u.inv_bc2 = (float)(1.0 / (1.0 - pow(u.beta2_d, t)));
   }
   if (u.rule == 0) {
-    const double n2 = norm2[ch.tensor];
+    const double n2 = tensor_norm2(chunk_norm, ch, s8);
     if (!isfinite(n2)) return;  // NaN/Inf gradient: skip this tensor's update
     const double nrm = sqrt(n2);
     if (nrm > (double)u.max_norm) scale = (float)((double)u.max_norm / nrm);
@@ -356,123 +459,17 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ pa
   const int64_t n4 = ch.len >> 2;
   float4* p4 = reinterpret_cast<float4*>(params + ch.off);
   const float4* g4 = reinterpret_cast<const float4*>(grads + ch.off);
-  if (u.opt == 0) {
-    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
-      float4 p = p4[i];
-      const float4 g = g4[i];
-      p.x -= u.lr * (g.x * scale);
-      p.y -= u.lr * (g.y * scale);
-      p.z -= u.lr * (g.z * scale);
-      p.w -= u.lr * (g.w * scale);
-      p4[i] = p;
-    }
-    trace_end(trace);
-    return;
-  }
   float4* m4 = reinterpret_cast<float4*>(m + ch.off);
   float4* v4 = reinterpret_cast<float4*>(v + ch.off);
   const float omb1 = 1.0f - u.beta1, omb2 = 1.0f - u.beta2;
   for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
-    float4 p = p4[i], mm = m4[i], vv = v4[i];
-    const float4 g = g4[i];
-    float pe[4] = {p.x, p.y, p.z, p.w}, me[4] = {mm.x, mm.y, mm.z, mm.w}, ve[4] = {vv.x, vv.y, vv.z, vv.w};
-    const float ge[4] = {g.x * scale, g.y * scale, g.z * scale, g.w * scale};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      me[k] = me[k] * u.beta1 + omb1 * ge[k];
-      ve[k] = ve[k] * u.beta2 + omb2 * (ge[k] * ge[k]);
-      const float mh = me[k] * u.inv_bc1;
-      float vh = ve[k] * u.inv_bc2;
-      if (u.rule == 0) vh = fmaxf(vh, u.eps2);
-      pe[k] -= u.lr * mh / (sqrtf(vh) + u.eps);
-    }
-    p4[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
-    m4[i] = make_float4(me[0], me[1], me[2], me[3]);
-    v4[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
+    float4 p = p4[i], mm = make_float4(0.f, 0.f, 0.f, 0.f), vv = mm;
+    if (u.opt == 1) { mm = m4[i]; vv = v4[i]; }
+    adam_or_sgd4(p, mm, vv, g4[i], scale, u, omb1, omb2);
+    p4[i] = p;
+    if (u.opt == 1) { m4[i] = mm; v4[i] = vv; }
   }
   trace_end(trace);
-}
-
-// K7 + update in one launch (CPU rule, networks whose chunks are all co-resident: host checks): every block keeps
-// its chunk's gradient in registers, adds its sum of squares to the tensor's norm, meets the other blocks at a
-// grid barrier, then clips and updates from the registers -- one launch and one read of the gradient less.
-// bar[0] counts block arrivals since the context was created (64-bit, never reset), bar[1] the launches.
-__global__ void __launch_bounds__(256, 4) norm_clip_update_kernel(float* __restrict__ params,
-                                                               const float* __restrict__ grads,
-                                                               float* __restrict__ m, float* __restrict__ v,
-                                                               const Chunk* __restrict__ chunks,
-                                                               double* __restrict__ norm2, UpdateParams u,
-                                                               unsigned long long* __restrict__ bar) {
-  pdl_wait();
-  const Chunk ch = chunks[blockIdx.x];
-  const int64_t n4 = ch.len >> 2;            // <= 512: two 128-bit elements per thread
-  const float4* g4 = reinterpret_cast<const float4*>(grads + ch.off);
-  float4 g[2];
-  float acc = 0.f;
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int64_t i = threadIdx.x + e * 256;
-    g[e] = (i < n4) ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    acc = fmaf(g[e].x, g[e].x, acc); acc = fmaf(g[e].y, g[e].y, acc);
-    acc = fmaf(g[e].z, g[e].z, acc); acc = fmaf(g[e].w, g[e].w, acc);
-  }
-  __shared__ double s[8];
-  const double d = warp_sum_d((double)acc);
-  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = d;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < 8; ++i) t += s[i];
-    atomicAdd(&norm2[ch.tensor], t);
-    // grid barrier: every block read bar[1] before it arrives, block 0 bumps it once all have arrived
-    const unsigned long long launch = *reinterpret_cast<volatile unsigned long long*>(bar + 1);
-    const unsigned long long target = (launch + 1ull) * gridDim.x;
-    __threadfence();
-    atomicAdd(bar, 1ull);
-    unsigned int polls = 0;
-    while (*reinterpret_cast<volatile unsigned long long*>(bar) < target) {
-      if (++polls > 64u) __nanosleep(32);
-      if (polls > (1u << 24)) __trap();   // blocks not co-resident: protocol bug, do not hang
-    }
-    __threadfence();
-    if (blockIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(bar + 1) = launch + 1ull;
-  }
-  __syncthreads();
-  pdl_launch_dependents();                   // only now: a dependent kernel's CTAs must never take slots this grid still needs
-  const double n2 = __ldcg(&norm2[ch.tensor]);
-  if (!isfinite(n2)) return;                 // NaN/Inf gradient: skip this tensor's update (gradient_decent.pyx:37-39)
-  const double nrm = sqrt(n2);
-  const float scale = (nrm > (double)u.max_norm) ? (float)((double)u.max_norm / nrm) : 1.0f;
-  float4* p4 = reinterpret_cast<float4*>(params + ch.off);
-  float4* m4 = reinterpret_cast<float4*>(m + ch.off);
-  float4* v4 = reinterpret_cast<float4*>(v + ch.off);
-  const float omb1 = 1.0f - u.beta1, omb2 = 1.0f - u.beta2;
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int64_t i = threadIdx.x + e * 256;
-    if (i >= n4) continue;
-    const float4 p = p4[i];
-    float pe[4] = {p.x, p.y, p.z, p.w};
-    const float ge[4] = {g[e].x * scale, g[e].y * scale, g[e].z * scale, g[e].w * scale};
-    if (u.opt == 0) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) pe[k] -= u.lr * ge[k];
-    } else {
-      const float4 mm = m4[i], vv = v4[i];
-      float me[4] = {mm.x, mm.y, mm.z, mm.w}, ve[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        me[k] = me[k] * u.beta1 + omb1 * ge[k];
-        ve[k] = ve[k] * u.beta2 + omb2 * (ge[k] * ge[k]);
-        const float mh = me[k] * u.inv_bc1;
-        const float vh = fmaxf(ve[k] * u.inv_bc2, u.eps2);
-        pe[k] -= u.lr * mh / (sqrtf(vh) + u.eps);
-      }
-      m4[i] = make_float4(me[0], me[1], me[2], me[3]);
-      v4[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
-    }
-    p4[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -506,18 +503,19 @@ __global__ void f32_padded_to_f32_kernel(const float* __restrict__ src, int64_t 
   }
 }
 
-// split-K fix-up: out = epilogue(acc) for GEMMs whose partial sums were accumulated with atomics.
-// epi: 0 none, 1 +bias, 2 relu(+bias), 3 mask by (act > 0)
-__global__ void gemm_fixup_kernel(float* __restrict__ c, int M, int N, int64_t ldc, int epi,
-                                  const float* __restrict__ bias, const float* __restrict__ mask,
-                                  int64_t ldmask) {
+// split-K without atomics (fallback when the k-slices cannot meet in distributed shared memory): out = epilogue(sum of the
+// S partial tiles in slice order).  epi: 0 none, 1 +bias, 2 relu(+bias), 3 mask by (act > 0)
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int S, int64_t part_stride, float* __restrict__ c,
+                                     int M, int N, int64_t ldc, int epi, const float* __restrict__ bias,
+                                     const float* __restrict__ mask, int64_t ldmask) {
   pdl_wait();
   pdl_launch_dependents();
   const int64_t total = (int64_t)M * N;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / N, n = i - r * N;
-    float v = c[r * ldc + n];
+    float v = 0.f;
+    for (int z = 0; z < S; ++z) v += __ldcg(ws + (int64_t)z * part_stride + r * ldc + n);
     if (epi == 1 || epi == 2) v += bias[n];
     if (epi == 2) v = (v < 0.f) ? 0.f : v;
     if (epi == 3) v = (mask[r * ldmask + n] <= 0.f) ? 0.f : v;

@@ -13,7 +13,8 @@
 //   warp 1 (1 thread)  MMA issuer: 4 x tcgen05.mma (K=8 each) per 32-wide k-block, tcgen05.commit
 //                      releases the smem stage / signals the epilogue
 //   warps 2-5          epilogue: tcgen05.ld (32 lanes x 32 cols) -> bias / ReLU / ReLU-mask ->
-//                      128-bit global stores, or red.global.add.v4.f32 for split-K partials
+//                      128-bit global stores; split-K slices that cannot meet in distributed shared memory store
+//                      their raw partial tiles side by side (summed in slice order by a later pass: no atomics)
 // K-major tiles are [rows][32 floats] with SWIZZLE_128B (SBO 1024 B); MN-major tiles are
 // [MN/32 atoms][32 k-rows][32 floats] in the SWIZZLE_128B_BASE32B form -- the only smem layout the
 // tensor core accepts for MN-major TF32 (32-B swizzle granules, 4 k-rows per atom; LBO = 4096 B between
@@ -43,14 +44,17 @@ struct TcGemmArgs {
   float* C;
   int64_t ldc;
   int M, N, K;
-  int epi;      // 0 none, 1 +bias, 2 relu(+bias), 3 mask (only when !atomic)
-  int atomic;   // 1: accumulate partial sums with red.add (split-K); epilogue applied by gemm_fixup_kernel
+  int epi;      // 0 none, 1 +bias, 2 relu(+bias), 3 mask (only when !partial)
+  int partial;  // 1: split-K slice z stores its raw partial tile at C + z * part_stride (no epilogue); the slices are
+                //    added in z order by grad_finalize_kernel (dW) or splitk_reduce_kernel (which applies the epilogue)
+  int64_t part_stride;
   int num_kb;        // total 32-wide k-blocks
   int kb_per_split;  // k-blocks per gridDim.z slice
   const float* bias;
   const float* mask;
   int64_t ldmask;
-  float* colsum;     // optional: colsum[n] += sum_m C[m,n] of the epilogue output (bias gradient), !atomic only
+  float* colsum_part;  // optional (bias gradient, !partial only): colsum_part[blockIdx.y * ld_colsum + n] = sum of the epilogue
+  int64_t ld_colsum;   //   output over this CTA's 128 rows -- one ordered partial per row tile, added by grad_finalize_kernel
   int cluster_reduce;  // 1: the gridDim.z k-slices of a tile share a cluster; partial tiles meet in distributed shared memory
   int pair;            // 1: two M-adjacent CTAs share a cluster; each loads half of the B tile and multicasts it to both
   // epi == 4 (output layer of a training step, N <= 32, one N tile): logits + bias -> softmax -> cross-entropy,
@@ -60,8 +64,8 @@ struct TcGemmArgs {
   const int32_t* labels;
   float* dz;
   int64_t lddz;
-  double* stats;
-  float* db;
+  unsigned long long* stats;
+  float* db_part;      // db_o partial of this row tile: db_part[blockIdx.y * lddz + j]
   StepBookkeeping bk;
   unsigned long long* trace;   // timeline slot (diagnostics) or nullptr
 };
@@ -89,10 +93,6 @@ __device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
-}
-
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // Cluster split-K tail (see the kernel): CTA `rank` of S finishes rows [rank*128/S, (rank+1)*128/S) of the tile.  A warp
@@ -315,11 +315,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if constexpr (BN == 32 && !A_MN && !B_MN) {
       if (g.epi == 4) {
         fused_softmax = true;
-        if (blockIdx.x == 0 && blockIdx.y == 0 && q == 0) {   // per-step housekeeping (see StepBookkeeping)
-          for (int i = lane; i < g.bk.n_norm; i += 32) g.bk.norm2[i] = 0.0;
-          if (g.bk.cursor && lane == 0) { g.bk.cursor[0] += g.bk.advance; g.bk.cursor[1] += 1; }
-        }
-        __syncwarp();
+        if (blockIdx.x == 0 && blockIdx.y == 0 && q == 0 && lane == 0) step_bookkeeping(g.bk);   // per-step housekeeping
         float v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), v);
         const int C = g.N;
@@ -360,16 +356,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         float correct = (valid && arg == y) ? 1.f : 0.f;
         loss = warp_sum_d(loss);
         correct = warp_sum(correct);
-        if (lane == 0) {
-          atomicAdd(&g.stats[0], loss);
-          atomicAdd(&g.stats[1], (double)correct);
-        }
+        if (lane == 0) stats_add(g.stats, loss, (unsigned long long)correct);
+        // db_o = column sums of dZ: per warp by shuffles, the four warps of the row tile meet in smem in warp order
+        // and the CTA stores ONE ordered partial (grad_finalize_kernel adds the row tiles in order)
+        float* cs_smem = reinterpret_cast<float*>(smem);
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j < C) {                                   // db_o = column sums of dZ over this warp's 32 rows
+          if (j < C) {
             const float cs = warp_sum(v[j]);
-            if (lane == 0) atomicAdd(g.db + j, cs);
+            if (lane == 0) cs_smem[q * 32 + j] = cs;
           }
+        asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
+        if (q == 0 && lane < (int)g.lddz) {
+          const float tot = (lane < C) ? ((cs_smem[lane] + cs_smem[32 + lane]) + (cs_smem[64 + lane] + cs_smem[96 + lane])) : 0.f;
+          g.db_part[(int64_t)blockIdx.y * g.lddz + lane] = tot;
+        }
       }
     }
     if (!fused_softmax) {
@@ -385,6 +386,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     __syncwarp();
     if (!g.cluster_reduce) {
+    float* const Cout = g.C + (g.partial ? (int64_t)blockIdx.z * g.part_stride : 0);
     const int row0 = m0 + q * 32;
     const int nrows = min(32, g.M - row0);            // warp-uniform, may be <= 0
     const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
@@ -402,7 +404,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const bool col_ok = cc < ncols;
       const int n = n0 + cc;
       float bias4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (col_ok && !g.atomic && (g.epi == 1 || g.epi == 2)) {
+      if (col_ok && !g.partial && (g.epi == 1 || g.epi == 2)) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) bias4[e] = (n + e < g.N) ? __ldg(g.bias + n + e) : 0.f;
       }
@@ -410,7 +412,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll 1
       for (int rb = 0; rb < 32; rb += U * RPI) {
         float mk[U][4];
-        if (g.epi == 3 && !g.atomic) {
+        if (g.epi == 3 && !g.partial) {
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int r = rb + u * RPI + lr;
@@ -432,8 +434,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (col_ok && r < nrows) {
             const float4 acc = *reinterpret_cast<const float4*>(stage + r * PITCH + cc);
             float o[4] = {acc.x, acc.y, acc.z, acc.w};
-            float* crow = g.C + (int64_t)(row0 + r) * g.ldc + n;
-            if (!g.atomic) {
+            float* crow = Cout + (int64_t)(row0 + r) * g.ldc + n;
+            if (!g.partial) {
               if (g.epi == 1 || g.epi == 2) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) o[e] += bias4[e];
@@ -450,27 +452,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               for (int e = 0; e < 4; ++e) cs[e] += o[e];
             }
             if (vec_ok) {   // columns in [N, round_up(N,4)) are padding of the row and receive exact zeros
-              if (g.atomic) red_add_v4(crow, o[0], o[1], o[2], o[3]);
-              else *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                if (n + e < g.N) {
-                  if (g.atomic) atomicAdd(crow + e, o[e]);
-                  else crow[e] = o[e];
-                }
+                if (n + e < g.N) crow[e] = o[e];
             }
           }
         }
       }
-      if (g.colsum && !g.atomic) {   // db[n] += sum over this warp's 32 rows (backward_pass.pyx:93)
+      if (g.colsum_part && !g.partial) {   // db[n] = sum over this warp's 32 rows (backward_pass.pyx:93)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
 #pragma unroll
           for (int o = LPR; o < 32; o <<= 1) cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], o);
         }
-        // per-warp sums meet in smem (behind the staging tiles) first: one global atomic per column per CTA instead
-        // of four -- the same-address atomics of 32 M-tiles x 4 warps were a 2-4 us completion tail of the dA GEMMs
+        // per-warp sums meet in smem (behind the staging tiles) in warp order; the CTA stores one ordered partial per
+        // column (same-address atomics of 32 M-tiles x 4 warps were also a 2-4 us completion tail of the dA GEMMs)
         if (lr == 0 && col_ok) {
           float* cs_smem = reinterpret_cast<float*>(smem) + 128 * PITCH + q * BN + cc;
 #pragma unroll
@@ -478,12 +476,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
     }
-    if (g.colsum && !g.atomic) {
+    if (g.colsum_part && !g.partial) {
       asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
       const float* cs_all = reinterpret_cast<const float*>(smem) + 128 * PITCH;
       for (int j = (warp - 2) * 32 + lane; j < ncols; j += 128) {
         const float tot = (cs_all[j] + cs_all[BN + j]) + (cs_all[2 * BN + j] + cs_all[3 * BN + j]);
-        if (n0 + j < g.N) atomicAdd(g.colsum + n0 + j, tot);
+        if (n0 + j < g.N) g.colsum_part[(int64_t)blockIdx.y * g.ld_colsum + n0 + j] = tot;
       }
     }
     }  // !cluster_reduce
@@ -581,10 +579,11 @@ struct GemmCall {
   const float* bias;
   const float* mask; int64_t ldmask;
   int cls;  // KernelClass
-  float* colsum;      // optional fused column sums of the output (must be zeroed by the caller)
-  bool c_is_zero;     // caller guarantees C is already zero (skips the split-K memset)
-  // epi == 4: fused softmax / cross-entropy / dZ epilogue of the output layer (C is not written)
-  const int32_t* labels; float* dz; int64_t lddz; double* stats; float* db; StepBookkeeping bk;
+  // Gradient outputs are ordered partial sums (elementwise.cuh: GradParts), 1-based tensor index, 0 = none:
+  int grad_slot;      // C is the gradient of tensor grad_slot-1: split-K slices go side by side into its arena region
+  int colsum_slot;    // fused column sums of the output (bias gradient of tensor colsum_slot-1): one partial per row tile
+  // epi == 4: fused softmax / cross-entropy / dZ epilogue of the output layer (C is not written); db_slot = bias tensor
+  const int32_t* labels; float* dz; int64_t lddz; unsigned long long* stats; int db_slot; StepBookkeeping bk;
   int max_ctas;       // > 0: cap tiles x split (a GEMM meant to run on the SMs another kernel leaves idle)
 };
 
@@ -658,9 +657,15 @@ static int dispatch_bn(pycnn_b200_ctx* c, int BN, const GemmCall& g, const CUten
   }
 }
 
-static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
-  PB_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "tc_gemm: empty problem");
-  PB_CHECK(!( !g.a_kmajor && g.b_kmajor), "tc_gemm: (A MN-major, B K-major) is not instantiated");
+struct GemmPlan {
+  int BN, tiles_m, tiles_n, num_kb, split, kb_per_split;
+  bool cluster, pair;
+};
+
+// Tiling of one GEMM: a pure function of the shape, the call's epilogue and the context's switches (ensure_workspace
+// sizes the partial-sum arena from the same function).
+static GemmPlan plan_tc_gemm(const pycnn_b200_ctx* c, const GemmCall& g) {
+  GemmPlan p{};
   int BN = g.N <= 32 ? 32 : g.N <= 64 ? 64 : g.N <= 128 ? 128 : 256;
   const int tiles_m = (int)ceil_div(g.M, tc::G_BM);
   const int num_kb = (int)ceil_div(g.K, tc::G_BK);
@@ -675,22 +680,19 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   }
   if (c->force_bn > 0 && num_kb > 16 && g.N >= c->force_bn) BN = c->force_bn;   // experiments (PYCNN_B200_FORCE_BN)
   const int tiles_n = (int)ceil_div(g.N, BN);
-  // deep-K problems whose tile grid cannot fill the 148 SMs: split K across gridDim.z, partial sums meet in
-  // red.global.add.v4.f32 (the epilogue is then applied by gemm_fixup_kernel)
+  // deep-K problems whose tile grid cannot fill the 148 SMs: split K across gridDim.z
   int split = 1;
   const int tiles = tiles_m * tiles_n;
-  PB_CHECK(g.epi != 4 || (g.N <= 32 && g.a_kmajor && g.b_kmajor && g.labels && g.dz && g.stats && g.db && (g.lddz & 3) == 0 && g.lddz <= 32),
-           "tc_gemm: the fused softmax epilogue needs N <= 32 and K-major operands");
-  if (tiles * 2 <= c->num_sms && num_kb >= 16 && !g.colsum && g.epi != 4) {
+  if (tiles * 2 <= c->num_sms && num_kb >= 16 && !g.colsum_slot && g.epi != 4) {
     split = (int)std::min<int64_t>(c->num_sms / tiles, num_kb / 4);
     if (split < 1) split = 1;
   }
   if (g.max_ctas > 0) split = std::max(1, std::min(split, g.max_ctas / std::max(1, tiles)));
   int kb_per_split = (int)ceil_div(num_kb, split);
   split = (int)ceil_div(num_kb, kb_per_split);  // no empty slices
-  // When the output needs an epilogue (or is not known to be zero) the k-slices of a tile run as one thread-block
-  // cluster and meet in distributed shared memory instead of in global atomics: no zero-fill, no fix-up pass,
-  // deterministic.  Needs a cluster size of 2/4/8 with no empty slice and all clusters resident at once.
+  // When the output needs an epilogue the k-slices of a tile run as one thread-block cluster and meet in distributed
+  // shared memory: no workspace, no second pass.  Needs a cluster size of 2/4/8 with no empty slice and all clusters
+  // resident at once.  Gradient outputs (grad_slot) keep the wide split and store ordered partials instead.
   // Deep-K problems with at least two M tiles also pair M-adjacent CTAs: both need the same B tile, each fetches
   // half of it and multicasts it to the pair (a third less L2->SM traffic per k-block for a 128 x 256 tile).
   const auto& occ = g_max_clusters[bn_slot(BN)][layout_slot(!g.a_kmajor, !g.b_kmajor)];
@@ -698,7 +700,7 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   const bool pair_ok = c->use_pair && tiles_m >= 2 && BN >= 64 && kb_per_split >= 64 && g.epi != 4;
   const int pair_tiles = tiles_n * (int)ceil_div(tiles_m, 2);
   bool cluster = false, pair = false;
-  if (split > 1 && (g.epi != 0 || !g.c_is_zero) && c->use_cluster_splitk) {
+  if (split > 1 && !g.grad_slot && c->use_cluster_splitk) {
     for (int si = 3; si >= 1 && !cluster; --si) {
       const int S = 1 << si;
       if (S > split) continue;
@@ -711,40 +713,74 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
     }
   }
   if (!cluster && pair_ok && occ[1][0] >= std::min(pair_tiles * split, c->num_sms / 2)) pair = true;
+  p.BN = BN; p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.num_kb = num_kb; p.split = split; p.kb_per_split = kb_per_split;
+  p.cluster = cluster; p.pair = pair;
+  return p;
+}
+
+static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
+  PB_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "tc_gemm: empty problem");
+  PB_CHECK(!( !g.a_kmajor && g.b_kmajor), "tc_gemm: (A MN-major, B K-major) is not instantiated");
+  PB_CHECK(g.epi != 4 || (g.N <= 32 && g.a_kmajor && g.b_kmajor && g.labels && g.dz && g.stats && g.db_slot && (g.lddz & 3) == 0 && g.lddz <= 32),
+           "tc_gemm: the fused softmax epilogue needs N <= 32 and K-major operands");
+  const GemmPlan p = plan_tc_gemm(c, g);
+  const int BN = p.BN, split = p.split;
+  const bool partial = split > 1 && !p.cluster;
   CUtensorMap ma, mb;
   if (g.a_kmajor) PB_TRY(make_map_kmajor(c, &ma, g.A, g.M, g.K, g.lda, tc::G_BM));
   else            PB_TRY(make_map_mnmajor(c, &ma, g.A, g.K, g.M, g.lda));
-  if (g.b_kmajor) PB_TRY(make_map_kmajor(c, &mb, g.B, g.N, g.K, g.ldb, pair ? BN / 2 : BN));
+  if (g.b_kmajor) PB_TRY(make_map_kmajor(c, &mb, g.B, g.N, g.K, g.ldb, p.pair ? BN / 2 : BN));
   else            PB_TRY(make_map_mnmajor(c, &mb, g.B, g.K, g.N, g.ldb));
-  tc::TcGemmArgs a;
+  dim3 grid(p.tiles_n, p.pair ? (unsigned)round_up(p.tiles_m, 2) : p.tiles_m, split);
+  tc::TcGemmArgs a{};
   a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.N = g.N; a.K = g.K;
-  a.epi = g.epi; a.atomic = split > 1 ? 1 : 0;
-  a.num_kb = num_kb; a.kb_per_split = kb_per_split;
+  a.epi = g.epi; a.partial = partial ? 1 : 0;
+  a.num_kb = p.num_kb; a.kb_per_split = p.kb_per_split;
   a.bias = g.bias; a.mask = g.mask; a.ldmask = g.ldmask;
-  a.colsum = g.colsum;
-  a.cluster_reduce = cluster ? 1 : 0;
-  a.pair = pair ? 1 : 0;
-  a.labels = g.labels; a.dz = g.dz; a.lddz = g.lddz; a.stats = g.stats; a.db = g.db; a.bk = g.bk;
-  a.trace = trace_slot(c, g.cls);
-  if (cluster) a.atomic = 0;
-  dim3 grid(tiles_n, pair ? (unsigned)round_up(tiles_m, 2) : tiles_m, split);
-  c->last_gemm_ctas = (int)(grid.x * grid.y * grid.z);
-  if (split > 1 && !g.c_is_zero && !cluster) {
-    LaunchScope ls(c, g.cls);   // the split-K zero-fill and fix-up are part of this GEMM's cost
-    PB_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * ((size_t)(g.M - 1) * g.ldc + g.N), c->stream));
+  a.cluster_reduce = p.cluster ? 1 : 0;
+  a.pair = p.pair ? 1 : 0;
+  a.labels = g.labels; a.dz = g.dz; a.lddz = g.lddz; a.stats = g.stats; a.bk = g.bk;
+  const int64_t tile_floats = (int64_t)(g.M - 1) * g.ldc + round_up(g.N, 4);
+  if (g.grad_slot) {                      // gradient tensor: ordered partials in its arena region (or C itself when unsplit)
+    GradPartSlot& gs = c->gp[g.grad_slot - 1];
+    gs.nparts = 0;
+    if (partial) {
+      PB_CHECK(split <= gs.cap && tile_floats <= gs.stride, "gradient partial arena too small for tensor %d (split %d, cap %d)", g.grad_slot - 1, split, gs.cap);
+      gs.nparts = split;
+      a.C = c->d_gpart + gs.off; a.part_stride = gs.stride;
+    }
+  } else if (partial) {                   // forward / dA fallback: shared workspace + ordered reduce with the epilogue below
+    a.part_stride = round_up(tile_floats, 4);
+    PB_CHECK(c->d_gemm_ws && (size_t)(a.part_stride * split) * sizeof(float) <= c->gemm_ws_bytes, "split-K workspace too small");
+    PB_CHECK(c->stream != c->side_stream, "the shared split-K workspace belongs to the main stream");
+    a.C = c->d_gemm_ws;
   }
+  if (g.colsum_slot) {
+    GradPartSlot& gs = c->gp[g.colsum_slot - 1];
+    PB_CHECK((int)grid.y <= gs.cap, "bias-gradient partial arena too small for tensor %d (%d row tiles, cap %d)", g.colsum_slot - 1, (int)grid.y, gs.cap);
+    gs.nparts = (int)grid.y;
+    a.colsum_part = c->d_gpart + gs.off; a.ld_colsum = gs.stride;
+  }
+  if (g.epi == 4) {
+    GradPartSlot& gs = c->gp[g.db_slot - 1];
+    PB_CHECK((int)grid.y <= gs.cap && gs.stride == g.lddz, "output-bias partial arena does not fit (%d row tiles, cap %d)", (int)grid.y, gs.cap);
+    gs.nparts = (int)grid.y;
+    a.db_part = c->d_gpart + gs.off;
+  }
+  a.trace = trace_slot(c, g.cls);
+  c->last_gemm_ctas = (int)(grid.x * grid.y * grid.z);
   {
     LaunchScope ls(c, g.cls);
     if (g.a_kmajor && g.b_kmajor) PB_TRY((dispatch_bn<false, false>(c, BN, g, ma, mb, a, grid)));
     else if (g.a_kmajor && !g.b_kmajor) PB_TRY((dispatch_bn<false, true>(c, BN, g, ma, mb, a, grid)));
     else PB_TRY((dispatch_bn<true, true>(c, BN, g, ma, mb, a, grid)));
   }
-  if (split > 1 && g.epi != 0 && !cluster) {
+  if (partial && !g.grad_slot) {
     LaunchScope ls(c, g.cls);
     const int64_t total = (int64_t)g.M * g.N;
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 8 * c->num_sms);
-    PB_CUDA(launch_pdl(c, gemm_fixup_kernel, dim3(blocks), dim3(256), 0, c->stream, g.C, g.M, g.N, g.ldc, g.epi, g.bias,
-                       g.mask, g.ldmask));
+    PB_CUDA(launch_pdl(c, splitk_reduce_kernel, dim3(blocks), dim3(256), 0, c->stream, (const float*)c->d_gemm_ws, split,
+                       a.part_stride, g.C, g.M, g.N, g.ldc, g.epi, g.bias, g.mask, g.ldmask));
   }
   return 0;
 }

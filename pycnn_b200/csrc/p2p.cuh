@@ -8,8 +8,9 @@
 //   A  p2p_reduce_kernel   rank r owns a contiguous range of the flat buffer's chunks; it waits for "grads
 //                          ready" flags from all ranks, sums its range over all ranks' gradient buffers with
 //                          128-bit loads across NVLink (fixed rank order: deterministic), stores the reduced
-//                          gradient locally and accumulates per-tensor ||g||^2 partials;        (reduce-scatter)
-//                          its last block publishes the partials to every peer;
+//                          gradient locally and one sum of squares per chunk;                  (reduce-scatter)
+//                          its last block adds them per tensor in chunk order (no atomics: bit-reproducible) and
+//                          publishes the partial ||g||^2 to every peer;
 //   C  p2p_update_kernel   waits for all ranks' partials and sums them in rank order (the norms of the fully
 //                          reduced gradient, identical on every rank); clip / skip / SGD / Adam on the owned range only (optimizer state is sharded: m and v
 //                          of a chunk are only ever touched by its owner) and 128-bit stores of the new
@@ -84,7 +85,8 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {
 // while attached, advanced by the last block of p2p_update_kernel), so flags only ever increase.
 __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chunk* __restrict__ chunks,
                                                          const long long* __restrict__ seq_ptr,
-                                                         double* __restrict__ norm_part, int ntensors,
+                                                         double* __restrict__ chunk_norm,
+                                                         const int2* __restrict__ tensor_chunks, int ntensors,
                                                          unsigned int* __restrict__ blocks_done,
                                                          unsigned long long* trace) {
   pdl_wait();
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chun
     if (threadIdx.x == 0) {
       double tot = 0.0;
       for (int i = 0; i < 8; ++i) tot += sh[i];
-      atomicAdd(&norm_part[ch.tensor], tot);
+      chunk_norm[t.chunk0 + blockIdx.x] = tot;
     }
   }
   // the last block to finish publishes this rank's per-tensor partial norms to every rank.  One fence per block,
@@ -146,15 +148,21 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chun
   }
   __syncthreads();
   if (last) {
-    for (int i = threadIdx.x; i < t.world * ntensors; i += blockDim.x) {
-      const int r = i / ntensors, k = i - r * ntensors;
-      t.sync[r]->norms[t.rank][k] = __ldcg(&norm_part[k]);
+    // per tensor: the owned chunks' sums of squares, added in chunk order by one warp (lanes stride the range, then a
+    // fixed shuffle tree) -- the same bits every run -- and stored into every rank's sync block
+    const int lane = threadIdx.x & 31;
+    for (int k = threadIdx.x >> 5; k < ntensors; k += (int)(blockDim.x >> 5)) {
+      const int2 tc = tensor_chunks[k];
+      const int lo = max(tc.x, t.chunk0), hi = min(tc.x + tc.y, t.chunk0 + t.nchunks);
+      double a = 0.0;
+      for (int i = lo + lane; i < hi; i += 32) a += __ldcg(&chunk_norm[i]);
+      a = warp_sum_d(a);
+      if (lane < t.world) t.sync[lane]->norms[t.rank][k] = a;
     }
     __syncthreads();
     if (threadIdx.x == 0) __threadfence_system();
     __syncthreads();
     if (threadIdx.x < t.world) st_release_sys(&t.sync[threadIdx.x]->norms_ready[t.rank], seq);
-    for (int k = threadIdx.x; k < ntensors; k += blockDim.x) norm_part[k] = 0.0;   // ready for the next step
     if (threadIdx.x == 0) *blocks_done = 0u;
   }
   trace_end(trace);
@@ -203,29 +211,11 @@ __global__ void __launch_bounds__(256) p2p_update_kernel(PeerTable t, const Chun
       float4* v4 = reinterpret_cast<float4*>(v + ch.off);
       const float omb1 = 1.0f - u.beta1, omb2 = 1.0f - u.beta2;
       for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
-        const float4 p = p4[i], g = g4[i];
-        float pe[4] = {p.x, p.y, p.z, p.w};
-        const float ge[4] = {g.x * scale, g.y * scale, g.z * scale, g.w * scale};
-        if (u.opt == 0) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) pe[k] -= u.lr * ge[k];
-        } else {
-          const float4 mm = m4[i], vv = v4[i];
-          float me[4] = {mm.x, mm.y, mm.z, mm.w}, ve[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            me[k] = me[k] * u.beta1 + omb1 * ge[k];
-            ve[k] = ve[k] * u.beta2 + omb2 * (ge[k] * ge[k]);
-            const float mh = me[k] * u.inv_bc1;
-            float vh = ve[k] * u.inv_bc2;
-            if (u.rule == 0) vh = fmaxf(vh, u.eps2);
-            pe[k] -= u.lr * mh / (sqrtf(vh) + u.eps);
-          }
-          m4[i] = make_float4(me[0], me[1], me[2], me[3]);
-          v4[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
-        }
-        const float4 np = make_float4(pe[0], pe[1], pe[2], pe[3]);
-        for (int r = 0; r < t.world; ++r) *(reinterpret_cast<float4*>(t.params[r] + ch.off) + i) = np;
+        float4 p = p4[i], mm = make_float4(0.f, 0.f, 0.f, 0.f), vv = mm;
+        if (u.opt == 1) { mm = m4[i]; vv = v4[i]; }
+        adam_or_sgd4(p, mm, vv, g4[i], scale, u, omb1, omb2);
+        if (u.opt == 1) { m4[i] = mm; v4[i] = vv; }
+        for (int r = 0; r < t.world; ++r) *(reinterpret_cast<float4*>(t.params[r] + ch.off) + i) = p;
       }
     }
   }
@@ -249,164 +239,12 @@ __global__ void __launch_bounds__(256) p2p_update_kernel(PeerTable t, const Chun
   trace_end(trace);
 }
 
-// ---- A + C in one launch (opt-in, PYCNN_B200_P2P_FUSED=1) ---------------------------------------------------
-// Same protocol, one kernel: a block keeps its reduced chunk in registers across the norm exchange, so the reduced
-// gradient is not re-read and one launch boundary disappears.  Every block waits (step 4) for flags that are only
-// posted once ALL blocks of every rank have finished step 2, so the whole grid must be co-resident: the host
-// launches this kernel only when nchunks fits the device (chunks are 2048 floats = two float4 per thread).
-__global__ void __launch_bounds__(256, 2) p2p_fused_kernel(PeerTable t, const Chunk* __restrict__ chunks,
-                                                           long long* __restrict__ seq_ptr,
-                                                           double* __restrict__ norm_part, int ntensors,
-                                                           float* __restrict__ m, float* __restrict__ v, UpdateParams u,
-                                                           unsigned int* __restrict__ blocks_done,
-                                                           unsigned long long* trace) {
-  pdl_wait();
-  trace_begin(trace);
-  const unsigned long long seq = (unsigned long long)seq_ptr[1] + 1ull;
-  // 1. gradients of every rank are complete
-  if (blockIdx.x == 0 && threadIdx.x < t.world) {
-    __threadfence_system();
-    st_release_sys(&t.sync[threadIdx.x]->grads_ready[t.rank], seq);
-  }
-  if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->grads_ready[threadIdx.x], seq);
-  __syncthreads();
-  // 2. reduce-scatter of the owned chunk into registers (fixed rank order), partial norm
-  __shared__ double sh[8];
-  __shared__ double s_n2;
-  __shared__ bool last;
-  const bool owns = (int)blockIdx.x < t.nchunks;
-  Chunk ch{};
-  float4 red[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-  int64_t n4 = 0;
-  if (owns) {
-    ch = chunks[t.chunk0 + blockIdx.x];
-    n4 = ch.len >> 2;
-    float4 part[2][MAX_RANKS];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int64_t i = threadIdx.x + e * 256;
-#pragma unroll
-      for (int r = 0; r < MAX_RANKS; ++r)
-        if (r < t.world && i < n4) part[e][r] = ld_peer(reinterpret_cast<const float4*>(t.grads[r] + ch.off) + i);
-    }
-    float acc = 0.f;
-    float4* mine = reinterpret_cast<float4*>(t.grads[t.rank] + ch.off);
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int64_t i = threadIdx.x + e * 256;
-      if (i < n4) {
-        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int r = 0; r < MAX_RANKS; ++r)
-          if (r < t.world) { sum.x += part[e][r].x; sum.y += part[e][r].y; sum.z += part[e][r].z; sum.w += part[e][r].w; }
-        red[e] = sum;
-        mine[i] = sum;     // get_grad() after a step still returns the reduced gradient
-        acc = fmaf(sum.x, sum.x, acc); acc = fmaf(sum.y, sum.y, acc); acc = fmaf(sum.z, sum.z, acc); acc = fmaf(sum.w, sum.w, acc);
-      }
-    }
-    const double d = warp_sum_d((double)acc);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = d;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double tot = 0.0;
-      for (int i = 0; i < 8; ++i) tot += sh[i];
-      atomicAdd(&norm_part[ch.tensor], tot);
-    }
-  }
-  // 3. the last block publishes this rank's partial norms to every rank
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    last = (atomicAdd(blocks_done, 1u) == gridDim.x - 1);
-    __threadfence();
-  }
-  __syncthreads();
-  if (last) {
-    for (int i = threadIdx.x; i < t.world * ntensors; i += blockDim.x) {
-      const int r = i / ntensors, k = i - r * ntensors;
-      t.sync[r]->norms[t.rank][k] = __ldcg(&norm_part[k]);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < t.world) st_release_sys(&t.sync[threadIdx.x]->norms_ready[t.rank], seq);
-    for (int k = threadIdx.x; k < ntensors; k += blockDim.x) norm_part[k] = 0.0;
-    if (threadIdx.x == 0) *blocks_done = 0u;
-  }
-  // 4.-5. norms of the fully reduced gradient, sharded clip + update from registers, all-gather of the parameters
-  if (owns) {
-    float scale = 1.0f;
-    bool skip = false;
-    if (u.rule == 0) {
-      if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->norms_ready[threadIdx.x], seq);
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        double n2 = 0.0;
-        for (int r = 0; r < t.world; ++r) n2 += __ldcv(&t.sync[t.rank]->norms[r][ch.tensor]);
-        s_n2 = n2;
-      }
-      __syncthreads();
-      const double n2 = s_n2;
-      if (!isfinite(n2)) skip = true;
-      const double nrm = sqrt(n2);
-      if (!skip && nrm > (double)u.max_norm) scale = (float)((double)u.max_norm / nrm);
-    }
-    if (u.rule == 1 && u.opt == 1) {
-      const double tt = (double)max((long long)u.steps_done[1], 1ll);
-      u.inv_bc1 = (float)(1.0 / (1.0 - pow(u.beta1_d, tt)));
-      u.inv_bc2 = (float)(1.0 / (1.0 - pow(u.beta2_d, tt)));
-    }
-    if (!skip) {
-      const float4* p4 = reinterpret_cast<const float4*>(t.params[t.rank] + ch.off);
-      float4* m4 = reinterpret_cast<float4*>(m + ch.off);
-      float4* v4 = reinterpret_cast<float4*>(v + ch.off);
-      const float omb1 = 1.0f - u.beta1, omb2 = 1.0f - u.beta2;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int64_t i = threadIdx.x + e * 256;
-        if (i >= n4) continue;
-        const float4 p = p4[i];
-        float pe[4] = {p.x, p.y, p.z, p.w};
-        const float ge[4] = {red[e].x * scale, red[e].y * scale, red[e].z * scale, red[e].w * scale};
-        if (u.opt == 0) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) pe[k] -= u.lr * ge[k];
-        } else {
-          const float4 mm = m4[i], vv = v4[i];
-          float me[4] = {mm.x, mm.y, mm.z, mm.w}, ve[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            me[k] = me[k] * u.beta1 + omb1 * ge[k];
-            ve[k] = ve[k] * u.beta2 + omb2 * (ge[k] * ge[k]);
-            const float mh = me[k] * u.inv_bc1;
-            float vh = ve[k] * u.inv_bc2;
-            if (u.rule == 0) vh = fmaxf(vh, u.eps2);
-            pe[k] -= u.lr * mh / (sqrtf(vh) + u.eps);
-          }
-          m4[i] = make_float4(me[0], me[1], me[2], me[3]);
-          v4[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
-        }
-        const float4 np = make_float4(pe[0], pe[1], pe[2], pe[3]);
-        for (int r = 0; r < t.world; ++r) *(reinterpret_cast<float4*>(t.params[r] + ch.off) + i) = np;
-      }
-    }
-  }
-  // 6. completion barrier across ranks
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    last = (atomicAdd(blocks_done + 1, 1u) == gridDim.x - 1);
-    __threadfence();
-  }
-  __syncthreads();
-  if (last) {
-    if (threadIdx.x == 0) blocks_done[1] = 0u;
-    if (threadIdx.x < t.world) st_release_sys(&t.sync[threadIdx.x]->params_done[t.rank], seq);
-    if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->params_done[threadIdx.x], seq);
-    __syncthreads();
-    if (threadIdx.x == 0) seq_ptr[1] = (long long)seq;
-  }
-  trace_end(trace);
+// Optimizer state is sharded in this mode (a rank only ever touches m, v of the chunks it owns).  Before the state is
+// read (checkpoints) or the exchange is left, every rank copies ITS range into a zeroed scratch buffer; an all-reduce
+// (sum of disjoint shards) then gives every rank the complete state.
+__global__ void owned_range_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int64_t lo, int64_t hi) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = (i >= lo && i < hi) ? src[i] : 0.f;
 }
 
 }  // namespace p2p

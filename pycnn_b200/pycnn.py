@@ -427,9 +427,12 @@ class PyCNN:
                               self.learning_rate, self.beta1, self.beta2, self.eps)
             self._opt_key = key
 
-    def optimizer_state(self):
-        """Adam m, v as float64 dicts (downloaded on demand; the reference keeps them in self.m/self.v)."""
+    def optimizer_state(self, _synced=False):
+        """Adam m, v as float64 dicts (downloaded on demand; the reference keeps them in self.m/self.v).
+        Data-parallel runs: a collective (every rank calls it)."""
         ctx = self._require()
+        if self._world > 1 and not _synced:
+            ctx.comm_sync_opt_state()
         wk, bk = self._keys()
         m, v = {}, {}
         for l, (w, b) in enumerate(zip(wk, bk)):
@@ -515,8 +518,8 @@ class PyCNN:
                       f"acc={epoch_acc:.4f}  loss={epoch_loss:.6f}   ", end="")
             if plot:
                 plot.update(epoch, epoch_loss, epoch_acc)
-            if checkpoint and self._rank == 0 and (epoch + 1) % max(1, int(checkpoint_every)) == 0:
-                self.save_checkpoint(checkpoint, epoch=epoch + 1, quiet=True)
+            if checkpoint and (epoch + 1) % max(1, int(checkpoint_every)) == 0:
+                self.save_checkpoint(checkpoint, epoch=epoch + 1, quiet=True)     # collective; rank 0 writes
             if epoch_loss <= 1e-6 and epoch_acc >= 0.999999 and epoch < self.epochs:
                 if self._rank == 0:
                     print(f"\nModel reached maximum learning on epoch {epoch}")
@@ -580,11 +583,16 @@ class PyCNN:
         """Additive sidecar to model.bin (whose dict layout is untouched, :688-706): the same model dict plus what
         the reference cannot restore -- Adam m, v, t, hyper-parameters, the epoch reached and the host NumPy RNG
         state that drives np.random.permutation (:622) -- so that load_checkpoint() + train_model(start_epoch=...)
-        continues the run it was taken from."""
+        continues the run it was taken from.  Data-parallel runs: every rank calls it (the sharded optimizer state
+        of the peer-memory exchange is gathered first); rank 0 writes the file."""
         ctx = self._require()
+        if self._world > 1:
+            ctx.comm_sync_opt_state()
+            if self._rank != 0:
+                return
         if self._params_on_device:
             self._pull_params()
-        m, v = self.optimizer_state() if self._opt_key is not None else ({}, {})
+        m, v = self.optimizer_state(_synced=True) if self._opt_key is not None else ({}, {})
         blob = {
             "format": self.CHECKPOINT_FORMAT,
             "model": {"weights": {k: np.asarray(x, dtype=np.float64) for k, x in self.weights.items()},

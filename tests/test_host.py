@@ -4,6 +4,7 @@ refuses to run without a GPU instead of falling back."""
 import contextlib
 import io
 import os
+import re
 import pickle
 import socket
 import subprocess
@@ -27,7 +28,7 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/pycnn_b200.h but not exported"
     assert set(names) == set(_lib._SIGNATURES), "ctypes binding and header disagree"
-    assert lib.pycnn_b200_abi_version() == 1
+    assert lib.pycnn_b200_abi_version() == _lib.ABI_VERSION == int(re.search(r"PYCNN_B200_ABI_VERSION (\d+)", open(_lib.HEADER_PATH).read()).group(1))
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     assert set(names) <= exported
