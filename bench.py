@@ -283,7 +283,7 @@ def run_ours(args):
         while done < nsteps:
             k = min(pool_steps, nsteps - done)
             perm = np.random.default_rng(done).permutation(pool)[:k * gbs] if shuffled else None
-            ctx.train_epoch_images(h_img.data_ptr(), h_lab.data_ptr(), k * gbs, S, gbs, perm=perm)
+            ctx.train_epoch_images(h_img.data_ptr(), h_lab.data_ptr(), k * gbs, S, gbs, perm=perm, num_images=pool)
             done += k
         ctx.event_record(3)
         ctx.synchronize()

@@ -214,8 +214,10 @@ int pycnn_b200_launch_count(pycnn_b200_ctx* ctx, int64_t* launches);
 /* write >= L2-size bytes to evict L2 between timed iterations */
 /* In-kernel timeline (diagnostics; no reference counterpart): op 0 = enable with `capacity` slots (drops captured graphs
  * so that new captures carry slots), 1 = reset all slots, 2 = disable.  Every traced launch (GEMMs, row gather, norm,
- * update) records {first CTA start, last CTA end} in %globaltimer ns; read returns the slots handed out so far:
- * times[2*i], times[2*i+1] and kinds[i] = kernel class + 100 * stream (0 main, 1 side, 2 prefetch). */
+ * update) records {first CTA start, last CTA end} in %globaltimer ns plus (min, max) over its CTAs of up to three
+ * phase marks (GEMMs: first operand stage landed, accumulator complete, partial tile parked); read returns the
+ * slots handed out so far: 8 words per slot in times[8*i .. 8*i+7] (unused marks: ~0 / 0) and
+ * kinds[i] = kernel class + 100 * stream (0 main, 1 side, 2 prefetch). */
 int pycnn_b200_trace_control(pycnn_b200_ctx* ctx, int op, int capacity);
 int pycnn_b200_trace_read(pycnn_b200_ctx* ctx, uint64_t* times, int32_t* kinds, int capacity, int* count);
 int pycnn_b200_flush_l2(pycnn_b200_ctx* ctx);

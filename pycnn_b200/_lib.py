@@ -305,20 +305,25 @@ class Context:
     def trace_disable(self):
         check(self.lib.pycnn_b200_trace_control(self.handle, 2, 0))
 
-    def trace_read(self):
-        """-> list of (kernel class name, stream id, start_ns, end_ns) in launch order; untouched slots are skipped."""
+    def trace_read(self, marks=False):
+        """-> list of (kernel class name, stream id, start_ns, end_ns) in launch order; untouched slots are skipped.
+        marks=True appends the three (min_ns, max_ns) phase-mark pairs (None when the kernel did not set them)."""
         cap = self._trace_cap
-        times = np.zeros(2 * cap, np.uint64)
+        times = np.zeros(8 * cap, np.uint64)
         kinds = np.zeros(cap, np.int32)
         n = ctypes.c_int()
         check(self.lib.pycnn_b200_trace_read(self.handle, ptr(times, ctypes.c_uint64), ptr(kinds, ctypes.c_int32), cap, ctypes.byref(n)))
         names = self.kernel_class_names()
         out = []
         for i in range(n.value):
-            t0, t1 = int(times[2 * i]), int(times[2 * i + 1])
+            t0, t1 = int(times[8 * i]), int(times[8 * i + 1])
             if t1 == 0:
                 continue
-            out.append((names[int(kinds[i]) % 100], int(kinds[i]) // 100, t0, t1))
+            row = (names[int(kinds[i]) % 100], int(kinds[i]) // 100, t0, t1)
+            if marks:
+                row += tuple((int(times[8 * i + 2 * k]), int(times[8 * i + 2 * k + 1])) if int(times[8 * i + 2 * k + 1]) else None
+                             for k in (1, 2, 3))
+            out.append(row)
         return out
 
     def set_step_count(self, t: int):

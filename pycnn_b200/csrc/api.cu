@@ -1810,8 +1810,8 @@ int pycnn_b200_launch_count(pycnn_b200_ctx* c, int64_t* launches) {
 }
 
 static int trace_fill(pycnn_b200_ctx* c) {
-  std::vector<unsigned long long> init(2 * (size_t)c->trace_cap);
-  for (int i = 0; i < c->trace_cap; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+  std::vector<unsigned long long> init(kTraceWords * (size_t)c->trace_cap);
+  for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;   // even words take minima, odd words maxima
   PB_CUDA(cudaMemcpy(c->d_trace, init.data(), sizeof(unsigned long long) * init.size(), cudaMemcpyHostToDevice));
   return 0;
 }
@@ -1823,7 +1823,7 @@ int pycnn_b200_trace_control(pycnn_b200_ctx* c, int op, int capacity) {
     PB_CHECK(capacity > 0 && capacity <= (1 << 20), "trace capacity %d out of range", capacity);
     drop_graphs(c);
     free_dev(c->d_trace); c->d_trace = nullptr;
-    PB_CUDA(cudaMalloc(&c->d_trace, sizeof(unsigned long long) * 2 * (size_t)capacity));
+    PB_CUDA(cudaMalloc(&c->d_trace, sizeof(unsigned long long) * kTraceWords * (size_t)capacity));
     c->trace_cap = capacity; c->trace_next = 0; c->trace_cls.clear(); c->trace = true;
     return trace_fill(c);
   }
@@ -1845,7 +1845,7 @@ int pycnn_b200_trace_read(pycnn_b200_ctx* c, uint64_t* times, int32_t* kinds, in
   PB_CHECK(c->d_trace, "trace is not enabled");
   PB_CUDA(cudaStreamSynchronize(c->stream));
   const int n = std::min(capacity, c->trace_next);
-  if (n > 0) PB_CUDA(cudaMemcpy(times, c->d_trace, sizeof(unsigned long long) * 2 * (size_t)n, cudaMemcpyDeviceToHost));
+  if (n > 0) PB_CUDA(cudaMemcpy(times, c->d_trace, sizeof(unsigned long long) * kTraceWords * (size_t)n, cudaMemcpyDeviceToHost));
   for (int i = 0; i < n; ++i) kinds[i] = c->trace_cls[i];
   *count = n;
   return 0;

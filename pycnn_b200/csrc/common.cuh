@@ -304,11 +304,21 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// A timeline slot is kTraceWords words: [0] min CTA start, [1] max CTA end, then (min, max) pairs of up to three
+// kernel-specific phase marks (GEMMs: first operand stage landed, accumulator complete; see gemm_tc.cuh).
+constexpr int kTraceWords = 8;
 __device__ __forceinline__ void trace_begin(unsigned long long* slot) {
   if (slot && threadIdx.x == 0) atomicMin(slot, global_timer_ns());
 }
 __device__ __forceinline__ void trace_end(unsigned long long* slot) {
   if (slot && threadIdx.x == 0) atomicMax(slot + 1, global_timer_ns());
+}
+__device__ __forceinline__ void trace_mark(unsigned long long* slot, int phase) {   // phase 1..3, one thread per CTA
+  if (slot) {
+    const unsigned long long t = global_timer_ns();
+    atomicMin(slot + 2 * phase, t);
+    atomicMax(slot + 2 * phase + 1, t);
+  }
 }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -349,7 +359,7 @@ static inline unsigned long long* trace_slot(pycnn_b200_ctx* c, int cls) {
   if (!c->trace || !c->d_trace || c->trace_next >= c->trace_cap) return nullptr;
   const int sid = (c->stream == c->side_stream) ? 1 : (c->stream == c->pf_stream) ? 2 : 0;
   c->trace_cls.push_back(cls + 100 * sid);
-  return c->d_trace + 2 * (size_t)(c->trace_next++);
+  return c->d_trace + kTraceWords * (size_t)(c->trace_next++);
 }
 
 static inline int ensure_scratch(pycnn_b200_ctx* c, size_t bytes) {

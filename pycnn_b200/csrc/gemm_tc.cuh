@@ -279,6 +279,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         fence_after_thread_sync();
+        if (i == 0) trace_mark(g.trace, 1);                       // first operand stage landed
         const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
@@ -311,6 +312,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float* stage = reinterpret_cast<float*>(smem) + q * 32 * PITCH;
     mbar_wait(tmem_full_bar, 0);
     fence_after_thread_sync();
+    if (threadIdx.x == 64) trace_mark(g.trace, 2);                // accumulator complete: the epilogue starts
     bool fused_softmax = false;
     if constexpr (BN == 32 && !A_MN && !B_MN) {
       if (g.epi == 4) {
@@ -488,6 +490,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }  // !fused_softmax
   }
   if (g.cluster_reduce) {
+    if (threadIdx.x == 64) trace_mark(g.trace, 3);                // partial tile parked in smem
     // Split-K without global partial sums: the gridDim.z CTAs of one output tile form a thread-block cluster, each
     // has parked its raw 128 x BN partial tile in its own shared memory (above).  After a cluster barrier CTA r sums
     // rows [r*128/S, (r+1)*128/S) over the S partials in rank order (deterministic) straight out of its peers'

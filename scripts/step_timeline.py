@@ -51,22 +51,23 @@ ctx.train_epoch(idx, BS)
 ctx.event_record(1)
 ctx.synchronize()
 ms = ctx.event_elapsed_ms(0, 1)
-ev = ctx.trace_read()
+ev = ctx.trace_read(marks=True)
 if rank != 0:
     ctx.close()
     sys.exit(0)
 print(f"# {steps} steps in {ms * 1e3:.1f} us = {ms * 1e3 / steps:.2f} us/step (CUDA events around train_epoch); "
       f"{len(ev)} traced launches")
 # a step starts at a layer-1 forward GEMM on the main stream
-starts = [i for i, e in enumerate(ev) if e[0] == "gemm_forward_layer1"]
 ev_sorted = sorted(ev, key=lambda e: e[2])
 starts_t = sorted(e[2] for e in ev if e[0] == "gemm_forward_layer1")
 if len(starts_t) >= 3:
     k = len(starts_t) // 2
     t0, t1 = starts_t[k], starts_t[k + 1]
     print(f"# step {k}: {(t1 - t0) / 1e3:.2f} us from its layer-1 GEMM start to the next one's")
-    print(f"{'kernel':24s} {'stream':>6s} {'start us':>9s} {'end us':>9s} {'dur us':>8s}")
-    for name, sid, a, b in ev_sorted:
+    print(f"{'kernel':24s} {'stream':>6s} {'start us':>9s} {'end us':>9s} {'dur us':>8s}   GEMM phase marks, us after the kernel's first CTA start (min..max over CTAs)")
+    for name, sid, a, b, *marks in ev_sorted:
         if t0 <= a < t1:
-            print(f"{name:24s} {sid:6d} {(a - t0) / 1e3:9.2f} {(b - t0) / 1e3:9.2f} {(b - a) / 1e3:8.2f}")
+            ph = "  ".join(f"{lbl} {(m[0] - a) / 1e3:.1f}..{(m[1] - a) / 1e3:.1f}" for lbl, m in
+                           zip(("first-stage", "accum-done", "parked"), marks) if m)
+            print(f"{name:24s} {sid:6d} {(a - t0) / 1e3:9.2f} {(b - t0) / 1e3:9.2f} {(b - a) / 1e3:8.2f}   {ph}")
 ctx.close()

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import pycnn_oracle as O
+from oracle import ref_kernels
 from tests.helpers import custom_filters, load_golden, rel_err, synth_images, synth_labels
 
 pytestmark = pytest.mark.gpu
@@ -309,6 +310,63 @@ def test_c1_trajectory_100_steps(lib, ctx, mode, opt, lr):
         assert np.isfinite(probs).all() and np.allclose(probs.sum(1), 1.0, atol=1e-5)
 
 
+HEADLINE_TRAJ_TOL = 5e-2      # measured value is printed; see DESIGN.md section 5
+
+
+@pytest.mark.skipif(not ref_kernels.available(), reason="oracle/_ref not built")
+def test_headline_trajectory_bs4096_adam_tf32(lib):
+    """The bench workload (BASELINE configs[1]: [4275,256,128,64,10], Adam lr 1e-4, batch 4096, TF32 tensor cores):
+    100 steps against the reference's own compiled kernels (oracle/_ref RefTrainer, float64) on identical rows --
+    both arms read the same feature values (the device matrix, widened to float64 for the CPU) -- and a repeat
+    run of the CUDA arm that must agree bit for bit."""
+    S, C, layers, bs, N, steps = 32, 10, [256, 128, 64], 4096, 16384, 100
+    labels = synth_labels(N, C, 11)
+
+    def cuda_run():
+        c = lib.Context(0)
+        c.set_math_mode(lib.MATH_TF32)
+        c.set_filters(O.DEFAULT_FILTERS)
+        D = c.feature_count(S)
+        c.set_network(D, layers, C)
+        w, b = O.init_layers(D, layers, C, seed=42)
+        wk, bk = O.layer_keys(len(layers))
+        for l, (wn, bn) in enumerate(zip(wk, bk)):
+            c.set_param(2 * l, w[wn])
+            c.set_param(2 * l + 1, b[bn])
+        c.set_optimizer(lib.OPT_ADAM, 1e-4)
+        c.dataset_alloc(N)
+        c.dataset_extract(0, synth_images(N, S, 10))
+        c.dataset_set_labels(0, labels)
+        rng = np.random.default_rng(12)
+        out = [c.train_step(rng.integers(0, N, bs)) for _ in range(steps)]
+        params = [c.get_param(i) for i in range(c.num_params())]
+        feats = c.dataset_get_features(0, N)
+        c.close()
+        return out, params, feats, (w, b)
+
+    out, params, feats, (w, b) = cuda_run()
+    out2, params2, _, _ = cuda_run()
+    assert out == out2, "TF32 training must be bit-reproducible"
+    for x, y in zip(params, params2):
+        np.testing.assert_array_equal(x, y)
+    ref = ref_kernels.RefTrainer(w, b, layers, 1e-4, "adam")
+    onehot = O.one_hot(labels, C)
+    rng = np.random.default_rng(12)
+    want = []
+    for _ in range(steps):
+        idx = rng.integers(0, N, bs)
+        want.append(ref.step(feats[idx], onehot[idx]))
+    got_l, want_l = np.array([o[0] for o in out]), np.array([o[0] for o in want])
+    dev = np.abs(got_l - want_l) / want_l
+    dcorr = max(abs(o[0 + 1] - r[1]) for o, r in zip(out, want))
+    wk, bk = O.layer_keys(len(layers))
+    perr = [rel_err(params[2 * l], ref.weights[wn]) for l, wn in enumerate(wk)]
+    print(f"\n[headline bs4096 adam tf32] 100-step loss trajectory vs oracle/_ref: max rel dev {dev.max():.3e} (step {dev.argmax()}), "
+          f"final loss/img {got_l[-1] / bs:.6f} vs {want_l[-1] / bs:.6f}, max |correct diff| {dcorr}, weight rel err {max(perr):.3e}")
+    assert dev.max() < HEADLINE_TRAJ_TOL
+    assert dcorr <= bs // 100
+
+
 def test_shard_sum_equals_full_batch_gradient(lib, ctx):
     """The data-parallel identity on one GPU: grads of two half batches add up to the full-batch
     gradient (sums, no 1/W scaling) -- what ncclSum over ranks reproduces."""
@@ -434,37 +492,6 @@ def test_large_config_shapes_step_parity(lib, ctx, mode, tol, name, S, F, C, lay
     if mode == "fp32":
         for l, wn in enumerate(wk):
             assert rel_err(ctx.get_param(2 * l), w[wn]) < 1e-4, wn
-
-
-def test_fused_tail_kernel_matches_per_layer_path(lib, monkeypatch):
-    """Opt-in fused MLP-tail forward kernel (csrc/mlp_tail.cuh) against the default per-layer path: same losses,
-    same parameters after three Adam steps (TF32 in both, so equal to TF32 noise)."""
-    S, C, layers, bs = 32, 10, [256, 128, 64], 512
-    imgs, lab = synth_images(bs, S, 41), synth_labels(bs, C, 42)
-    out = []
-    for fused in ("0", "1"):
-        monkeypatch.setenv("PYCNN_B200_FUSED_TAIL", fused)
-        c = lib.Context(0)
-        c.set_math_mode(lib.MATH_TF32)
-        c.set_filters(O.DEFAULT_FILTERS)
-        D = c.feature_count(S)
-        c.set_network(D, layers, C)
-        w, b = O.init_layers(D, layers, C, seed=42)
-        wk, bk = O.layer_keys(len(layers))
-        for l, (wn, bn) in enumerate(zip(wk, bk)):
-            c.set_param(2 * l, w[wn])
-            c.set_param(2 * l + 1, b[bn])
-        c.set_optimizer(lib.OPT_ADAM, 1e-4)
-        c.dataset_alloc(bs)
-        c.dataset_extract(0, imgs)
-        c.dataset_set_labels(0, lab)
-        stats = [c.train_step(np.arange(bs)) for _ in range(3)]
-        out.append((stats, [c.get_param(i) for i in range(c.num_params())]))
-        c.close()
-    for (l0, c0), (l1, c1) in zip(out[0][0], out[1][0]):
-        assert abs(l0 - l1) < 5e-3 * abs(l0) and abs(c0 - c1) <= 8
-    for a, bb in zip(out[0][1], out[1][1]):
-        assert rel_err(bb, a) < 2e-2
 
 
 def test_streamed_image_step_equals_resident_step(lib, ctx):
@@ -593,7 +620,7 @@ def _epoch_run(lib, env, monkeypatch, mode, opt, n=2100, bs=128, epochs=2, S=32,
     """`epochs` epochs over n rows (short last batch) in a fresh context created under `env`; returns per-epoch
     (loss, correct) and the final parameters."""
     for k in ("PYCNN_B200_PREFETCH", "PYCNN_B200_GRAPH_STEPS", "PYCNN_B200_FUSE_SOFTMAX", "PYCNN_B200_CLUSTER_SPLITK",
-              "PYCNN_B200_FORK", "PYCNN_B200_FUSE_UPDATE", "PYCNN_B200_GRAPHS", "PYCNN_B200_CARVEOUT", "PYCNN_B200_DEFER_DW"):
+              "PYCNN_B200_FORK", "PYCNN_B200_PDL", "PYCNN_B200_GRAPHS", "PYCNN_B200_CARVEOUT", "PYCNN_B200_DEFER_DW"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -619,24 +646,55 @@ def _epoch_run(lib, env, monkeypatch, mode, opt, n=2100, bs=128, epochs=2, S=32,
 
 
 @pytest.mark.parametrize("env", [{"PYCNN_B200_GRAPH_STEPS": "1"}, {"PYCNN_B200_GRAPH_STEPS": "4"}, {"PYCNN_B200_FORK": "0"},
-                                 {"PYCNN_B200_GRAPHS": "0"}, {"PYCNN_B200_FUSE_UPDATE": "1"}, {"PYCNN_B200_DEFER_DW": "0"}, {}],
-                         ids=["graph1", "graph4", "nofork", "eager", "fused_update", "nodefer", "default"])
-def test_step_scheduling_does_not_change_results(lib, monkeypatch, env):
-    """Row-gather prefetch, multi-step graphs, fork/join and the fused norm+update only reschedule the step: two
-    FP32 SGD epochs (17 batches each, short last one) give the plain one-stream path's losses and parameters."""
-    base_stats, base_params = _epoch_run(lib, {"PYCNN_B200_PREFETCH": "0", "PYCNN_B200_FORK": "0"}, monkeypatch, "fp32", "sgd")
-    stats, params = _epoch_run(lib, env, monkeypatch, "fp32", "sgd")
-    for (l0, c0), (l1, c1) in zip(base_stats, stats):
-        assert abs(l0 - l1) <= 1e-6 * abs(l0) and c0 == c1
+                                 {"PYCNN_B200_GRAPHS": "0"}, {"PYCNN_B200_DEFER_DW": "0"}, {"PYCNN_B200_PDL": "0"}, {}],
+                         ids=["graph1", "graph4", "nofork", "eager", "nodefer", "nopdl", "default"])
+@pytest.mark.parametrize("mode,opt", [("fp32", "sgd"), ("tf32", "adam")])
+def test_step_scheduling_does_not_change_results(lib, monkeypatch, env, mode, opt):
+    """Row-gather prefetch, multi-step graphs, fork/join, PDL only reschedule the step.  Gradients are ordered partial
+    sums (no atomics), so two epochs (17 batches each, short last one) reproduce the plain one-stream path BIT FOR BIT
+    -- except DEFER_DW=0 in TF32 mode, which changes how many k-slices dW of layer 2 is split into."""
+    base_stats, base_params = _epoch_run(lib, {"PYCNN_B200_PREFETCH": "0", "PYCNN_B200_FORK": "0"}, monkeypatch, mode, opt)
+    stats, params = _epoch_run(lib, env, monkeypatch, mode, opt)
+    if mode == "tf32" and "PYCNN_B200_DEFER_DW" in env:
+        for (l0, c0), (l1, c1) in zip(base_stats, stats):
+            assert abs(l0 - l1) <= 2e-3 * abs(l0) and abs(c0 - c1) <= 16
+        return
+    assert stats == base_stats
     for a, bb in zip(base_params, params):
-        assert rel_err(bb, a) < 1e-5          # float atomics in the bias-gradient column sums: order-dependent last bits
+        np.testing.assert_array_equal(bb, a)
+
+
+@pytest.mark.parametrize("S,bs,layers", [(8, 32, (16,)), (8, 7, (24, 8)), (12, 64, (32,))])
+def test_prefetch_pipeline_visits_every_row_once(lib, monkeypatch, S, bs, layers):
+    """Short rows and small batches: the row gather of step i+1 (prefetch stream, owns the device row cursor) finishes
+    while step i's output-layer epilogue does its bookkeeping on the main stream.  A lost cursor advance would train
+    one batch twice and drop the last one: the pipelined epoch must equal the unpipelined one exactly."""
+    kw = dict(n=2100, bs=bs, epochs=3, S=S, layers=layers)
+    for mode, opt in (("fp32", "sgd"), ("tf32", "adam")):
+        want = _epoch_run(lib, {"PYCNN_B200_PREFETCH": "0"}, monkeypatch, mode, opt, **kw)
+        got = _epoch_run(lib, {}, monkeypatch, mode, opt, **kw)
+        assert got[0] == want[0]
+        for a, bb in zip(want[1], got[1]):
+            np.testing.assert_array_equal(bb, a)
+
+
+@pytest.mark.parametrize("mode,opt", [("tf32", "adam"), ("tf32", "sgd"), ("fp32", "adam")])
+def test_training_is_bit_reproducible(lib, monkeypatch, mode, opt):
+    """BASELINE configs[1] shapes (batch 4096: dW of layer 1 runs as 4 k-slices, the shallow dW as 32): two runs in
+    fresh contexts give identical losses, counts and parameters -- no float atomics anywhere in the step."""
+    kw = dict(n=3 * 4096 + 1000, bs=4096, epochs=2, layers=(256, 128, 64))
+    a = _epoch_run(lib, {}, monkeypatch, mode, opt, **kw)
+    b = _epoch_run(lib, {}, monkeypatch, mode, opt, **kw)
+    assert a[0] == b[0]
+    for x, y in zip(a[1], b[1]):
+        np.testing.assert_array_equal(x, y)
 
 
 @pytest.mark.parametrize("env", [{"PYCNN_B200_FUSE_SOFTMAX": "0"}, {"PYCNN_B200_CLUSTER_SPLITK": "0"}],
-                         ids=["softmax_kernel", "atomic_splitk"])
+                         ids=["softmax_kernel", "workspace_splitk"])
 def test_fused_epilogues_match_separate_kernels(lib, monkeypatch, env):
-    """TF32 path: softmax/CE in the output-layer GEMM epilogue vs softmax_ce_kernel, cluster (DSMEM) split-K vs global
-    atomics + fix-up pass -- same losses and parameters up to TF32 / summation-order noise."""
+    """TF32 path: softmax/CE in the output-layer GEMM epilogue vs softmax_ce_kernel, cluster (DSMEM) split-K vs the
+    workspace + ordered-reduce fallback -- same losses and parameters up to TF32 / summation-order noise."""
     base_stats, base_params = _epoch_run(lib, {}, monkeypatch, "tf32", "sgd", layers=(256, 64))
     stats, params = _epoch_run(lib, env, monkeypatch, "tf32", "sgd", layers=(256, 64))
     for (l0, c0), (l1, c1) in zip(base_stats, stats):
