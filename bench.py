@@ -1,24 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the PyCNN hot path on B200 (contract: see the task's bench section).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c4]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
 
-Workload (BASELINE.json configs[1], the configuration `metric` is quoted on): CIFAR-10-shaped synthetic
-32x32 RGB, 10 classes, layers [256,128,64], Adam (lr 1e-4), batch 4096 per GPU; weak scaling for N > 1
-(global batch 4096*N, one NCCL all-reduce of the flat gradient per step).  A "step" is one pass of the
+Workloads (BASELINE.json `configs`; default c1 = configs[1], the configuration `metric` is quoted on):
+  c1  32x32 RGB, 10 classes, layers [256,128,64], Adam lr 1e-4, batch 4096 per GPU
+  c2  64x64 RGB, 100 classes, layers [1024,512,256], Adam, batch 4096 per GPU          (configs[2])
+  c4  224x224 RGB, custom 8-filter bank, 1000 classes, layers [2048,1024,512], Adam, batch 512 per GPU (configs[4])
+Weak scaling for N > 1 (global batch = batch x N, one gradient exchange per step).  A "step" is one pass of the
 reference's batch loop (pycnn/pycnn.py:629-642: gather, forward, CE/argmax, backward, update).
 
-  value  device-resident: the feature matrix (65536 x 4275 fp32, 1.1 GB > L2) lives in HBM; each step
-         gathers 4096 fresh random rows.  CUDA events on the library's compute stream, max over ranks.
+  value  device-resident: the feature matrix (> L2) lives in HBM; each step gathers fresh random rows.  MEDIAN of
+         5 repeats of the K-step region, each bracketed by barrier + synchronize, CUDA events on the library's
+         compute stream, max over ranks.
   e2e    the same step through the C ABI with HOST buffers: pinned uint8 images + int32 labels are
          copied H2D, the fused extractor produces the features, the step runs, loss/#correct come back.
-  roofline / cpu_baseline: see DESIGN.md "Measurement".
+  roofline / cpu_baseline / loss_check / dp_parity: see DESIGN.md "Measurement".
 One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -31,13 +35,64 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-S, C, LAYERS, BS, N_RESIDENT, LR = 32, 10, [256, 128, 64], 4096, 65536, 1e-4
-F = 19
-D = ((S - 2) // 2) ** 2 * F                                                    # 4275
-DIMS = [D] + LAYERS + [C]
-FWD_FLOP_PER_IMG = 2 * sum(a * b for a, b in zip(DIMS[:-1], DIMS[1:]))          # 2.272 MFLOP
-TRAIN_FLOP_PER_IMG = 3 * FWD_FLOP_PER_IMG - 2 * DIMS[0] * DIMS[1]               # 4.627 MFLOP (no dA for layer 1)
-EXTRACT_BYTES_PER_IMG = S * S * 3 + 4 * D                                       # 20172 B (u8 in + f32 out)
+REPEATS = 5
+CONFIGS = {
+    "c1": dict(tag="BASELINE configs[1]", S=32, C=10, layers=[256, 128, 64], bs=4096, resident=65536, lr=1e-4, F=19),
+    "c2": dict(tag="BASELINE configs[2]", S=64, C=100, layers=[1024, 512, 256], bs=4096, resident=16384, lr=1e-4, F=19),
+    "c4": dict(tag="BASELINE configs[4]", S=224, C=1000, layers=[2048, 1024, 512], bs=512, resident=2048, lr=1e-4, F=8),
+}
+
+
+class Workload:
+    """Shapes and algorithmic FLOPs / bytes of one BASELINE configuration."""
+
+    def __init__(self, key):
+        c = CONFIGS[key]
+        self.key, self.tag = key, c["tag"]
+        self.S, self.C, self.layers, self.bs, self.resident, self.lr, self.F = (c[k] for k in ("S", "C", "layers", "bs", "resident", "lr", "F"))
+        self.D = ((self.S - 2) // 2) ** 2 * self.F
+        self.dims = [self.D] + self.layers + [self.C]
+        self.fwd_flop_per_img = 2 * sum(a * b for a, b in zip(self.dims[:-1], self.dims[1:]))
+        self.train_flop_per_img = 3 * self.fwd_flop_per_img - 2 * self.dims[0] * self.dims[1]      # no dA for layer 1
+        self.extract_bytes_per_img = self.S * self.S * 3 + 4 * self.D                              # u8 in + f32 out
+        self.n_params = sum(a * b + b for a, b in zip(self.dims[:-1], self.dims[1:]))
+
+    def filters(self, arm="ours"):
+        if self.F == 19:                                                 # the reference's default 19-filter bank (pycnn/pycnn.py:71-91)
+            if arm == "ours":
+                from pycnn_b200.pycnn import PyCNN
+                return PyCNN().filters
+            from oracle import pycnn_oracle as O                          # CPU arm: the oracle's restatement of the same table
+            return O.DEFAULT_FILTERS
+        return np.round(np.random.default_rng(2).uniform(-2, 2, (self.F, 3, 3)), 3).tolist()   # SURVEY 8d custom bank
+
+    def string(self):
+        """The SAME string in both arms (`config.workload`)."""
+        bank = "default 19-filter bank" if self.F == 19 else f"custom {self.F}-filter bank"
+        return (f"{self.tag}: {self.S}x{self.S}x3 synthetic, {bank}, {self.C} classes, layers {self.layers}, Adam lr {self.lr:g}, "
+                f"batch {self.bs} per GPU, CPU update rule (clip 5, frozen t)")
+
+    def config(self, world):
+        """`config` of the JSON line: identical in the `ours` and `reference` arms."""
+        gb = self.resident * ((self.D + 3) // 4 * 4) * 4 / 1e9
+        return {"workload": self.string(), "global_batch": self.bs * world, "feature_dim": self.D,
+                "parallelism": f"dp{world}" if world > 1 else "single",
+                "l2": f"inputs larger than L2: {gb:.2f} GB resident fp32 feature matrix, fresh random rows every step"}
+
+    def init_params(self):
+        """The reference's seeded He init (pycnn/pycnn.py:225, :303-311): [(W, b)] per layer."""
+        np.random.seed(42)
+        out, prev = [], self.D
+        for size in self.layers + [self.C]:
+            w = np.random.randn(size, prev) * (2 / prev) ** 0.5
+            out.append((w, np.random.randn(size) * 0.01))
+            prev = size
+        return out
+
+    def check_batch(self, n):
+        """The fixed rows both arms' loss checks train on: n images + labels from one seeded stream."""
+        rng = np.random.default_rng(1000)
+        return rng.integers(0, 256, (n, self.S, self.S, 3), dtype=np.uint8), rng.integers(0, self.C, n).astype(np.int32)
 
 
 def peaks():
@@ -48,6 +103,40 @@ def peaks():
         return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
                     bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def measure_tf32_peak(torch, device):
+    """TF32 tensor-core peak measured in THIS process: cuBLAS fp32 GEMM with TF32 math, 8192^3.
+    burst = best of 10 single launches (the denominator for a kernel timed alone), sustained = back to back for ~1.5 s."""
+    torch.backends.cuda.matmul.allow_tf32 = True
+    n = 8192
+    with torch.cuda.device(device):
+        a = torch.randn(n, n, device="cuda")
+        b = torch.randn(n, n, device="cuda")
+        for _ in range(3):
+            torch.matmul(a, b)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(1500.0 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        sustained_ms = e0.elapsed_time(e1) / reps
+        del a, b
+        torch.cuda.empty_cache()
+    flop = 2.0 * n ** 3
+    return {"burst_tflops": flop / best / 1e9, "sustained_tflops": flop / sustained_ms / 1e9,
+            "how": f"torch.matmul fp32 inputs, allow_tf32 (cuBLAS TF32), {n}^3: best of 10 launches / {reps} back to back, same process"}
 
 
 class ClockSampler:
@@ -119,32 +208,51 @@ class ClockSampler:
                 "source": "nvml in-process" if self.nvml else "nvidia-smi"}
 
 
-def synth_model(lib, device):
-    """Context with the default bank, the C2 network initialised from the reference's seeded stream."""
-    from pycnn_b200.pycnn import PyCNN
+def load_params(ctx, lib, wl, params=None):
+    """(Re)load the seeded init and reset the optimizer (Adam m, v, t = 0)."""
+    for l, (w, b) in enumerate(params or wl.init_params()):
+        ctx.set_param(2 * l, w)
+        ctx.set_param(2 * l + 1, b)
+    ctx.set_optimizer(lib.OPT_ADAM, wl.lr)
+
+
+def synth_model(lib, device, wl, params=None):
     ctx = lib.Context(device)
     ctx.set_math_mode(lib.MATH_TF32)
     ctx.set_extract_mode(lib.EXTRACT_TC)
-    ctx.set_filters(PyCNN().filters)                                 # the reference's default 19-filter bank
-    ctx.set_network(D, LAYERS, C)
-    np.random.seed(42)                                               # pycnn/pycnn.py:225, :303-311
-    prev = D
-    for l, size in enumerate(LAYERS + [C]):
-        ctx.set_param(2 * l, np.random.randn(size, prev) * (2 / prev) ** 0.5)
-        ctx.set_param(2 * l + 1, np.random.randn(size) * 0.01)
-        prev = size
-    ctx.set_optimizer(lib.OPT_ADAM, LR)
+    ctx.set_filters(wl.filters())
+    ctx.set_network(wl.D, wl.layers, wl.C)
+    load_params(ctx, lib, wl, params)
     return ctx
 
 
+def fill_dataset(ctx, wl, rows):
+    """The same synthetic dataset on every rank (the design replicates it; each rank trains its slice of a batch)."""
+    rng = np.random.default_rng(1000)
+    ctx.dataset_alloc(rows)
+    chunk = max(1, min(rows, (192 << 20) // (wl.S * wl.S * 3)))
+    for s in range(0, rows, chunk):
+        m = min(chunk, rows - s)
+        ctx.dataset_extract(s, rng.integers(0, 256, (m, wl.S, wl.S, 3), dtype=np.uint8))
+    ctx.dataset_set_labels(0, np.random.default_rng(1001).integers(0, wl.C, rows).astype(np.int32))
+    return chunk
+
+
+def params_of(ctx):
+    return np.concatenate([ctx.get_param(i).ravel() for i in range(ctx.num_params())])
+
+
 def run_ours(args):
-    import torch                                                      # plumbing: pinned memory, process group
+    import torch                                                      # plumbing: pinned memory, process group, cuBLAS peak
     from pycnn_b200 import _lib as lib
     from pycnn_b200 import parallel
+    wl = Workload(args.config)
+    S, C, BS, D = wl.S, wl.C, wl.bs, wl.D
     rank, world, local = parallel.dist_env()
     if world > 1:
         parallel.init_process_group("nccl")
-    ctx = synth_model(lib, local)
+    init = wl.init_params()
+    ctx = synth_model(lib, local, wl, init)
     dp_mode = "single"
     if world > 1:
         uid = parallel.broadcast_bytes(lib.comm_unique_id() if rank == 0 else None)
@@ -154,18 +262,13 @@ def run_ours(args):
             parallel.attach_peer_memory(ctx, rank, world)
 
     sampler = ClockSampler(local) if rank == 0 else None      # NVML up and polling well before the timed regions
-    # ---------------- resident dataset: extract N_RESIDENT synthetic images on the device
-    rng = np.random.default_rng(1000 + rank)
-    ctx.dataset_alloc(N_RESIDENT)
-    for s in range(0, N_RESIDENT, 16384):
-        ctx.dataset_extract(s, rng.integers(0, 256, (16384, S, S, 3), dtype=np.uint8))
-    ctx.dataset_set_labels(0, rng.integers(0, C, N_RESIDENT).astype(np.int32))
+    first_chunk = fill_dataset(ctx, wl, wl.resident)
 
     K, W = args.steps, args.warmup
-    gbs = BS * world                                                  # weak scaling: 4096 per GPU
+    gbs = BS * world                                                  # weak scaling: BS per GPU
     idx_rng = np.random.default_rng(7)                                # identical on every rank
-    warm_idx = idx_rng.integers(0, N_RESIDENT, W * gbs)
-    timed_idx = idx_rng.integers(0, N_RESIDENT, K * gbs)
+    warm_idx = idx_rng.integers(0, wl.resident, W * gbs)
+    timed_idx = idx_rng.integers(0, wl.resident, K * gbs)
 
     def barrier():
         ctx.synchronize()
@@ -174,107 +277,49 @@ def run_ours(args):
         ctx.synchronize()
 
     t_load0 = time.time()                                      # clock samples: warm-up .. end of the e2e loops
-    if W:
-        ctx.train_epoch(warm_idx, gbs)
-    # the W contract warm-up steps are ~1 ms of GPU work: clocks, TLBs and the graph executable are not settled
-    # yet (first timed regions measured 10-50 % slower than steady state), so run two more untimed K-step passes
-    extra_warm = 2 * K
-    for _ in range(2):
-        ctx.train_epoch(timed_idx, gbs)
-    barrier()
-    launches0 = ctx.launch_count()
-    t0 = time.time()
-    ctx.event_record(0)
-    loss_sum, correct = ctx.train_epoch(timed_idx, gbs)               # K steps, one host sync at the end
-    ctx.event_record(1)
-    barrier()
-    t1 = time.time()
-    ms = ctx.event_elapsed_ms(0, 1)
-    launches = ctx.launch_count() - launches0
-    if world > 1:
-        ms = parallel.allreduce_scalars([ms], op="max")[0]
+    ctx.train_epoch(warm_idx, gbs)                             # W untimed warm-up steps (graph capture included)
+    # REPEATS timed regions of exactly K steps each; the reported time is their median
+    rep_ms, launches, loss_sum = [], 0, 0.0
+    for r in range(REPEATS):
+        barrier()
+        l0 = ctx.launch_count()
+        ctx.event_record(0)
+        loss_sum, _ = ctx.train_epoch(timed_idx, gbs)          # K steps, one host sync at the end
+        ctx.event_record(1)
+        barrier()
+        ms_r = ctx.event_elapsed_ms(0, 1)
+        if world > 1:
+            ms_r = parallel.allreduce_scalars([ms_r], op="max")[0]
+        rep_ms.append(ms_r)
+        launches = ctx.launch_count() - l0
+    ms = float(np.median(rep_ms))
     value = K * gbs / (ms / 1e3)
-    if os.environ.get("PYCNN_B200_BENCH_REPEATS"):       # diagnostics: run-to-run spread of the same K-step region
-        reps = []
-        for _ in range(int(os.environ["PYCNN_B200_BENCH_REPEATS"])):
-            barrier()
-            ctx.event_record(4)
-            ctx.train_epoch(timed_idx, gbs)
-            ctx.event_record(5)
-            barrier()
-            reps.append(round(ctx.event_elapsed_ms(4, 5) / K, 5))
-        if rank == 0:
-            print("repeat ms/step:", reps, file=sys.stderr, flush=True)
 
     # ---------------- per-kernel-class timing (events around every launch) for the roofline
     ctx.set_kernel_timing(True)
     ctx.kernel_stats(reset=True)
-    ctx.train_epoch(timed_idx[:min(K, 10) * gbs], gbs)
+    nsteps_prof = min(K, 10)
+    ctx.train_epoch(timed_idx[:nsteps_prof * gbs], gbs)
     stats = ctx.kernel_stats(reset=True)
     ctx.set_kernel_timing(False)
-    nsteps_prof = min(K, 10)
     per_class = {k: {"launches_per_step": n / nsteps_prof, "ms_per_step": t / nsteps_prof}
                  for k, (n, t) in stats.items() if n}
-    pk = peaks()
-    gemm_classes = ("gemm_forward_layer1", "gemm_dW_layer1", "gemm_forward_tail", "gemm_dA", "gemm_dW_tail")
-    l1_flop = 2 * BS * DIMS[0] * DIMS[1]                                       # 8.96 GFLOP: one layer-1 GEMM
-    class_flops = {"gemm_forward_layer1": l1_flop, "gemm_dW_layer1": l1_flop,
-                   "gemm_forward_tail": BS * FWD_FLOP_PER_IMG - l1_flop, "gemm_dW_tail": BS * FWD_FLOP_PER_IMG - l1_flop,
-                   "gemm_dA": BS * FWD_FLOP_PER_IMG - l1_flop}
-    n_params = sum(a * b + b for a, b in zip(DIMS[:-1], DIMS[1:]))
-    class_bytes = {"gather_rows": 2 * BS * (D + 1) * 4, "clip_update": 28 * n_params, "grad_sqnorm": 4 * n_params,
-                   "extract_conv_relu_pool": BS * EXTRACT_BYTES_PER_IMG}
-    tf32_peak = pk["bf16_tflops_sustained"] / 2.0
-
-    # DRAM bytes per launch from the committed ncu --set full captures of this same command (profiles/, cold L2)
-    ncu_names = {"gemm_forward_layer1": "gemm_tf32_kernel<256, 0, 0> (1, 32, 4)", "gemm_dW_layer1": "gemm_tf32_kernel<256, 1, 1> (17, 2, 4)",
-                 "gather_rows": "gather_rows_kernel (296, 1, 1)", "clip_update": "clip_update_kernel (560, 1, 1)",
-                 "grad_sqnorm": "grad_sqnorm_kernel (560, 1, 1)"}
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
-            ncu_traffic = json.load(f)["bytes_per_launch"]
-    except (OSError, ValueError, KeyError):
-        ncu_traffic = {}
-
-    def traffic_of(k):
-        return ncu_traffic.get(ncu_names.get(k, ""))
-
-    def roofline_of(k):
-        """algorithmic FLOPs (or bytes) of one launch / average CUDA-event duration of one launch of class k"""
-        ms_launch = per_class[k]["ms_per_step"] / per_class[k]["launches_per_step"]
-        if k in class_flops:
-            ach = class_flops[k] / per_class[k]["ms_per_step"] / 1e9          # whole class per step (TFLOP/s)
-            return {"kernel": k, "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-                    "frac": ach / tf32_peak, "traffic": traffic_of(k), "us_per_launch": ms_launch * 1e3,
-                    "peak_source": f"{pk['source']} bf16 sustained / 2 (tf32 runs at half the bf16 rate)"}
-        ach = class_bytes.get(k, 0) / per_class[k]["ms_per_step"] / 1e6          # GB/s
-        return {"kernel": k, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": traffic_of(k), "us_per_launch": ms_launch * 1e3, "peak_source": pk["source"]}
-
-    # dominant kernel: the single-kernel class with the largest share of the step (the "tail" classes are groups of
-    # several tiny latency-bound GEMMs and are reported in rooflines_all); a split-K GEMM's zero-fill and fix-up
-    # launches are charged to that GEMM
-    single = [k for k in ("gemm_forward_layer1", "gemm_dW_layer1", "gather_rows", "clip_update") if k in per_class]
-    dom = max(single, key=lambda k: per_class[k]["ms_per_step"])
-    roofline = roofline_of(dom)
-    roofline["note"] = "CUDA-event time around each launch of this kernel in an eager (non-graph) pass of the same steps"
-    rooflines_all = {k: roofline_of(k) for k in per_class if k in class_flops or k in class_bytes}
-    gemm_ms = sum(per_class[k]["ms_per_step"] for k in gemm_classes if k in per_class)
-    mlp_tflops = BS * TRAIN_FLOP_PER_IMG / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None
 
     # ---------------- e2e: host uint8 images -> H2D -> extractor -> step -> D2H stats, every step
     # pycnn_b200_train_epoch_images: every step's batch crosses PCIe from pinned host memory (copy stream),
     # overlapped with extractor + step of the previous batch (compute stream); the running loss/#correct are
     # copied back to the host after every step.
-    pool_steps = max(1, min(K, 32, (1 << 30) // (gbs * S * S * 3)))   # <= 1 GB of pinned host memory per rank
+    img_bytes = S * S * 3
+    pool_steps = max(1, min(K, 32, (1 << 30) // (gbs * img_bytes)))   # <= 1 GB of pinned host memory per rank
     pool = pool_steps * gbs
+    rng = np.random.default_rng(2000 + rank)
     h_img = torch.empty((pool, S, S, 3), dtype=torch.uint8, pin_memory=True)
     h_lab = torch.empty((pool,), dtype=torch.int32, pin_memory=True)
     h_img.numpy()[:] = rng.integers(0, 256, (pool, S, S, 3), dtype=np.uint8)
     h_lab.numpy()[:] = rng.integers(0, C, pool).astype(np.int32)
 
     def e2e_run(nsteps, shuffled):
-        """nsteps global batches (each rank trains on its 1/world slice of every batch, gradients all-reduce
+        """nsteps global batches (each rank trains on its 1/world slice of every batch, gradients exchanged
         per step) streamed from this rank's pinned pool; returns (ms, launches)."""
         l0 = ctx.launch_count()
         ctx.event_record(2)
@@ -292,60 +337,140 @@ def run_ours(args):
 
     e2e_run(max(W, 3), False)
     e2e_run(max(W, 3), True)
-    barrier()
-    e2e_ms, e2e_launches = e2e_run(K, False)
+    e2e_reps, e2e_launches = [], 0
+    for r in range(REPEATS):
+        barrier()
+        m, e2e_launches = e2e_run(K, False)
+        if world > 1:
+            m = parallel.allreduce_scalars([m], op="max")[0]
+        e2e_reps.append(m)
     barrier()
     e2e_shuf_ms, _ = e2e_run(K, True)
     barrier()
+    if world > 1:
+        e2e_shuf_ms = parallel.allreduce_scalars([e2e_shuf_ms], op="max")[0]
+    e2e_ms = float(np.median(e2e_reps))
+    e2e_value = K * gbs / (e2e_ms / 1e3)
+    e2e_shuf_value = K * gbs / (e2e_shuf_ms / 1e3)
     # extractor kernel alone, timed by events around its launches (eager, outside the graphs)
     ctx.set_kernel_timing(True)
     ctx.kernel_stats(reset=True)
     for i in range(5):
-        ctx.train_step_images(None, None, True, h_img.data_ptr() + (i % pool_steps) * BS * S * S * 3,
+        ctx.train_step_images(None, None, True, h_img.data_ptr() + (i % pool_steps) * BS * img_bytes,
                               h_lab.data_ptr() + (i % pool_steps) * BS * 4, BS, S)
     ex_stats = ctx.kernel_stats(reset=True)
     ctx.set_kernel_timing(False)
-    if world > 1:
-        e2e_ms, e2e_shuf_ms = parallel.allreduce_scalars([e2e_ms, e2e_shuf_ms], op="max")
-    e2e_value = K * gbs / (e2e_ms / 1e3)
-    e2e_shuf_value = K * gbs / (e2e_shuf_ms / 1e3)
     clocks = sampler.stop(t_load0, time.time()) if sampler else None
     ex_n, ex_ms = ex_stats.get("extract_conv_relu_pool", (0, 0.0))
-    ex_gbs = (BS * EXTRACT_BYTES_PER_IMG) / (ex_ms / max(ex_n, 1) * 1e-3) / 1e9 if ex_n else None
+    ex_gbs = (BS * wl.extract_bytes_per_img) / (ex_ms / max(ex_n, 1) * 1e-3) / 1e9 if ex_n else None
 
-    out = {
-        "metric": "train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
-        "warmup": W, "extra_untimed_warmup_steps": extra_warm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: 32x32x3 synthetic, 10 classes, layers [256,128,64], Adam lr 1e-4, "
-                               "batch 4096 per GPU, CPU update rule (clip 5, frozen t)",
-                   "global_batch": gbs, "resident_rows": N_RESIDENT, "feature_dim": D,
-                   "parallelism": f"dp{world}" if world > 1 else "single",
-                   "gradient_exchange": {"single": "none", "p2p": "fused peer-memory reduce-scatter/update/all-gather (NVLink, CUDA IPC)",
-                                         "nccl": "ncclAllReduce(sum) of the flat gradient + replicated update"}[dp_mode],
-                   "l2": "inputs larger than L2: 1.1 GB resident fp32 feature matrix, fresh random rows every step",
-                   "math_mode": "tf32 tcgen05 (fp32 accumulate)", "extractor": "default 19-filter bank"},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": BS * S * S * 3 + BS * 4,
-                "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / K, "gpu_launches": int(e2e_launches),
-                "path": "pycnn_b200_train_epoch_images: per step, pinned uint8 batch -> H2D (copy stream) -> fused "
-                        "extractor -> train step -> (loss,correct) D2H; copy of batch i+1 overlaps compute of batch i",
-                "shuffled_rows_value": e2e_shuf_value,
-                "shuffled_rows_path": "same, batch rows picked by a random permutation: zero-copy gather kernel over PCIe"},
-        "gpu_launches": int(launches),
-        "roofline": roofline,
-        "kernels_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in per_class.items()},
-        "rooflines_all": {k: {"frac": round(v["frac"], 4), "achieved": round(v["achieved"], 1), "unit": v["unit"],
-                              "us_per_launch": round(v["us_per_launch"], 2)} for k, v in rooflines_all.items()},
-        "mlp_gemm_tflops": mlp_tflops,
-        "roofline_extractor": None if ex_gbs is None else {
-            "bound": "hbm", "achieved": ex_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ex_gbs / pk["hbm_gbs"],
-            "frac_of_8TBps_nominal": ex_gbs / 8000.0, "images_per_s": BS / (ex_ms / ex_n * 1e-3),
-            "bytes_per_image": EXTRACT_BYTES_PER_IMG},
-        "final_loss_per_image": loss_sum / (K * gbs),
-    }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(seconds=args.cpu_seconds)
+    # ---------------- in-graph timeline of one step (first CTA start -> last CTA end per launch, %globaltimer)
+    timeline = None
+    ctx.trace_enable(4096)                         # collective under DP: every rank replays the same steps
+    nt = min(K, 16)
+    for _ in range(2):
+        ctx.train_epoch(timed_idx[:nt * gbs], gbs)
+    ctx.trace_reset()
+    ctx.train_epoch(timed_idx[:nt * gbs], gbs)
+    ev = ctx.trace_read()
+    ctx.trace_disable()
+    starts = sorted(e[2] for e in ev if e[0] == "gemm_forward_layer1")
+    if len(starts) >= 3:
+        k = len(starts) // 2
+        t0, t1 = starts[k], starts[k + 1]
+        acc = {}
+        for name, sid, a, b in ev:
+            if t0 <= a < t1:
+                acc.setdefault(name, []).append((b - a) / 1e3)
+        timeline = {"step_us": (t1 - t0) / 1e3, "kernel_us": {k2: [round(x, 2) for x in v] for k2, v in acc.items()},
+                    "how": "middle step of a multi-step graph; per launch: first CTA start to last CTA end (%globaltimer)"}
+
+    # ---------------- TF32 peak measured in this process, then the roofline
+    pk = peaks()
+    tf32 = measure_tf32_peak(torch, local) if rank == 0 else None
+    out = None
+    if rank == 0:
+        gemm_classes = ("gemm_forward_layer1", "gemm_dW_layer1", "gemm_forward_tail", "gemm_dA", "gemm_dW_tail")
+        l1_flop = 2 * BS * wl.dims[0] * wl.dims[1]                                  # one layer-1 GEMM launch
+        tail_flop = BS * wl.fwd_flop_per_img - l1_flop
+        class_flops = {"gemm_forward_layer1": l1_flop, "gemm_dW_layer1": l1_flop,
+                       "gemm_forward_tail": tail_flop, "gemm_dW_tail": tail_flop, "gemm_dA": tail_flop}
+        class_bytes = {"gather_rows": 2 * BS * (D + 1) * 4, "clip_update": 28 * wl.n_params, "grad_finalize": 8 * wl.n_params,
+                       "extract_conv_relu_pool": BS * wl.extract_bytes_per_img}
+        traffic = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+                traffic = json.load(f).get(wl.key, {})
+        except (OSError, ValueError):
+            pass
+
+        def roofline_of(k):
+            """algorithmic FLOPs (or bytes) of one launch / average CUDA-event duration of one launch of class k"""
+            ms_launch = per_class[k]["ms_per_step"] / per_class[k]["launches_per_step"]
+            if k in class_flops:
+                ach = class_flops[k] / per_class[k]["ms_per_step"] / 1e9          # whole class per step (TFLOP/s)
+                return {"kernel": k, "bound": "tensor", "achieved": ach, "peak": tf32["burst_tflops"], "unit": "TFLOP/s",
+                        "frac": ach / tf32["burst_tflops"], "traffic": traffic.get(k), "us_per_launch": ms_launch * 1e3,
+                        "peak_source": "TF32 GEMM timed in this process (burst: the kernel is bracketed alone by events)"}
+            ach = class_bytes.get(k, 0) / per_class[k]["ms_per_step"] / 1e6          # GB/s
+            return {"kernel": k, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "traffic": traffic.get(k), "us_per_launch": ms_launch * 1e3,
+                    "peak_source": f"{pk['source']} HBM copy bandwidth (MEASURED_PEAKS.json)"}
+
+        # dominant kernel: the single-kernel class with the largest share of the step (the "tail" classes are groups of
+        # several small GEMMs and are reported in rooflines_all)
+        single = [k for k in ("gemm_forward_layer1", "gemm_dW_layer1", "gather_rows", "clip_update") if k in per_class]
+        dom = max(single, key=lambda k: per_class[k]["ms_per_step"])
+        roofline = roofline_of(dom)
+        roofline["note"] = "CUDA-event time around each launch of this kernel in an eager (non-graph) pass of the same steps"
+        if timeline and dom in timeline["kernel_us"]:
+            us = float(np.mean(timeline["kernel_us"][dom]))
+            roofline["in_graph_us"] = us
+            if dom in class_flops:
+                roofline["in_graph_frac_of_sustained_peak"] = class_flops[dom] / us / 1e6 / tf32["sustained_tflops"]
+        rooflines_all = {k: roofline_of(k) for k in per_class if k in class_flops or k in class_bytes}
+        gemm_ms = sum(per_class[k]["ms_per_step"] for k in gemm_classes if k in per_class)
+        out = {
+            "metric": "train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32", "data": "synthetic", "config": wl.config(world),
+            "timing": {"repeats": REPEATS, "statistic": "median", "repeat_ms_per_step": [round(x / K, 6) for x in rep_ms]},
+            "arm_detail": {"resident_rows": wl.resident, "math_mode": "tf32 tcgen05 (fp32 accumulate)",
+                           "gradient_exchange": {"single": "none", "p2p": "fused peer-memory reduce-scatter/update/all-gather (NVLink, CUDA IPC)",
+                                                 "nccl": "ncclAllReduce(sum) of the flat gradient + replicated update"}[dp_mode]},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": BS * img_bytes + BS * 4,
+                    "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms / K, "gpu_launches": int(e2e_launches),
+                    "repeat_ms_per_step": [round(x / K, 6) for x in e2e_reps],
+                    "path": "pycnn_b200_train_epoch_images: per step, pinned uint8 batch -> H2D (copy stream) -> fused "
+                            "extractor -> train step -> (loss,correct) D2H; copy of batch i+1 overlaps compute of batch i",
+                    "shuffled_rows_value": e2e_shuf_value,
+                    "shuffled_rows_path": "same, batch rows picked by a random permutation: zero-copy gather kernel over PCIe"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "tf32_peak": tf32,
+            "kernels_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in per_class.items()},
+            "rooflines_all": {k: {"frac": round(v["frac"], 4), "achieved": round(v["achieved"], 1), "unit": v["unit"],
+                                  "us_per_launch": round(v["us_per_launch"], 2)} for k, v in rooflines_all.items()},
+            "mlp_gemm_tflops": BS * wl.train_flop_per_img / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
+            "step_tflops": BS * wl.train_flop_per_img / (ms / K * 1e-3) / 1e12,
+            "timeline": timeline,
+            "roofline_extractor": None if ex_gbs is None else {
+                "bound": "hbm", "achieved": ex_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ex_gbs / pk["hbm_gbs"],
+                "frac_of_8TBps_nominal": ex_gbs / 8000.0, "images_per_s": BS / (ex_ms / ex_n * 1e-3),
+                "bytes_per_image": wl.extract_bytes_per_img, "images_per_launch": BS},
+            "final_loss_per_image": loss_sum / (K * gbs),
+        }
+
+    # ---------------- parity legs, outside every timed region
+    if world > 1:
+        dp = dp_parity(ctx, lib, wl, init, rank, world, local, gbs, min(first_chunk, wl.resident))
+        if rank == 0:
+            out["dp_parity"] = dp
+    elif not args.no_cpu_baseline:
+        cb, cpu_losses = cpu_baseline(wl, seconds=args.cpu_seconds)
+        out["cpu_baseline"] = cb
+        out["loss_check"] = loss_check(ctx, lib, wl, init, cpu_losses, min(W, 3) + K)
     ctx.close()
     if world > 1:
         torch.distributed.barrier()
@@ -354,26 +479,75 @@ def run_ours(args):
         print(json.dumps(out))
 
 
-def make_cpu_trainer(batch):
+def loss_check(ctx, lib, wl, init, cpu_losses, replay_steps):
+    """The SAME rows in both arms: the fixed batch the CPU arm trains on (Workload.check_batch) goes through the
+    streaming step (H2D, extractor, step) from the same seeded init; per-step losses are compared with the CPU
+    arm's, and the loss after `replay_steps` steps is what `--impl reference --steps K --warmup W` prints too."""
+    imgs, labels = wl.check_batch(wl.bs)
+    load_params(ctx, lib, wl, init)
+    n = max(len(cpu_losses), replay_steps)
+    gpu = [ctx.train_step_images(imgs, labels)[0] / wl.bs for _ in range(n)]
+    m = min(len(cpu_losses), n)
+    dev = [abs(g - c) / abs(c) for g, c in zip(gpu[:m], cpu_losses[:m])]
+    return {"rows": f"{wl.bs} images + labels from default_rng(1000), the batch of the cpu_baseline / reference arm, same seeded init",
+            "steps_compared": m, "max_rel_dev_vs_cpu": max(dev) if dev else None,
+            "gpu_loss_per_image_at_last_compared_step": gpu[m - 1] if m else None,
+            "cpu_loss_per_image_at_last_compared_step": cpu_losses[m - 1] if m else None,
+            "replay_steps": replay_steps, "final_loss_per_image": gpu[replay_steps - 1]}
+
+
+def dp_parity(ctx, lib, wl, init, rank, world, local, gbs, rows, steps=6):
+    """Correctness signal for the scaling run: from the same seeded init, `steps` global batches through the
+    data-parallel path; (a) every rank must end with byte-identical parameters, (b) losses and parameters must match a
+    single-GPU replay of the same global batches on rank 0's GPU (TF32: equal up to summation order)."""
+    import torch.distributed as dist
+    load_params(ctx, lib, wl, init)
+    idx = np.random.default_rng(99).integers(0, rows, steps * gbs)
+    loss_dp, corr_dp = ctx.train_epoch(idx, gbs)
+    p_dp = params_of(ctx)
+    digests = [None] * world
+    dist.all_gather_object(digests, hashlib.sha256(p_dp.tobytes()).hexdigest())
+    res = None
+    if rank == 0:
+        single = synth_model(lib, local, wl, init)
+        fill_dataset(single, wl, rows)
+        loss_1, corr_1 = single.train_epoch(idx, gbs)
+        p_1 = params_of(single)
+        single.close()
+        perr = float(np.abs(p_dp - p_1).max() / np.abs(p_1).max())
+        lerr = abs(loss_dp - loss_1) / abs(loss_1)
+        identical = len(set(digests)) == 1
+        res = {"ok": bool(identical and lerr < 1e-3 and perr < 2e-2), "ranks_identical_params": identical, "steps": steps,
+               "loss_per_image_dp": loss_dp / (steps * gbs), "loss_per_image_single_gpu": loss_1 / (steps * gbs),
+               "loss_rel_dev": lerr, "correct_dp": int(corr_dp), "correct_single_gpu": int(corr_1),
+               "param_max_rel_err": perr, "how": "same seeded init and rows; single-GPU replay of the same global batches on rank 0"}
+    dist.barrier()
+    return res
+
+
+def make_cpu_trainer(wl, batch):
     """The reference's CPU path on the same workload: compiled Cython/C kernels from oracle/_ref when
-    present (kind 'reference'), else the numpy restatement (kind 'port')."""
+    present (kind 'reference'), else the numpy restatement (kind 'port').  step() returns the batch loss per image."""
     from oracle import pycnn_oracle as O
     from oracle import ref_kernels
-    rng = np.random.default_rng(1000)
-    imgs = rng.integers(0, 256, (min(batch, 4096), S, S, 3), dtype=np.uint8)
-    feats = O.extract_batch(imgs)
-    if batch > len(feats):
-        feats = np.concatenate([feats] * (batch // len(feats)))
-    y = O.one_hot(rng.integers(0, C, batch), C)
-    w, b = O.init_layers(D, LAYERS, C, seed=42)
+    imgs, labels = wl.check_batch(min(batch, wl.bs))
+    feats = O.extract_batch(imgs, wl.filters("oracle"))
+    y = O.one_hot(labels, wl.C)
+    if batch > len(feats):                                   # N > 1 reference arm: the global batch tiles the same rows
+        reps = batch // len(feats)
+        feats, y = np.concatenate([feats] * reps), np.concatenate([y] * reps)
+    wk, bk = O.layer_keys(len(wl.layers))
+    w = {k: p[0].copy() for k, p in zip(wk, wl.init_params())}
+    b = {k: p[1].copy() for k, p in zip(bk, wl.init_params())}
+    n = len(feats)
     if ref_kernels.available():
-        tr = ref_kernels.RefTrainer(w, b, LAYERS, LR, "adam")
-        return "reference", (lambda: tr.step(feats, y))
+        tr = ref_kernels.RefTrainer(w, b, wl.layers, wl.lr, "adam")
+        return "reference", (lambda: tr.step(feats, y)[0] / n)
     m, v = {}, {}
     for d in (w, b):
         for k in d:
             m[k], v[k] = np.zeros(d[k].shape), np.zeros(d[k].shape)
-    return "port", (lambda: O.train_step(feats, y, w, b, LAYERS, LR, "adam", m, v))
+    return "port", (lambda: O.train_step(feats, y, w, b, wl.layers, wl.lr, "adam", m, v)[0] / n)
 
 
 def cpu_threads():
@@ -403,25 +577,22 @@ class all_host_threads:
         return False
 
 
-def cpu_baseline(seconds=12.0):
+def cpu_baseline(wl, seconds=12.0):
+    """-> (cpu_baseline dict, per-step losses per image from the seeded init on the fixed check batch)"""
     with all_host_threads():
-        return _cpu_baseline(seconds)
-
-
-def _cpu_baseline(seconds):
-    kind, step = make_cpu_trainer(BS)
-    step()
-    n, t0 = 0, time.perf_counter()
-    while True:
-        step()
-        n += 1
-        el = time.perf_counter() - t0
-        if (el >= seconds and n >= 3) or n >= 400:
-            break
-    return {"value": n * BS / el, "unit": "images/s", "cores": cpu_threads(), "kind": kind,
-            "sample": f"{n} train steps of batch {BS} (features precomputed, as in the reference's train_model) "
-                      f"in {el:.1f} s on the host; os.cpu_count()={os.cpu_count()}",
-            "ms_per_step": el / n * 1e3}
+        kind, step = make_cpu_trainer(wl, wl.bs)
+        losses = [step()]                                    # first step: untimed (page faults, BLAS thread start-up)
+        n, t0 = 0, time.perf_counter()
+        while True:
+            losses.append(step())
+            n += 1
+            el = time.perf_counter() - t0
+            if (el >= seconds and n >= 3) or n >= 400:
+                break
+        return {"value": n * wl.bs / el, "unit": "images/s", "cores": cpu_threads(), "kind": kind,
+                "sample": f"{n} train steps of batch {wl.bs} (features precomputed, as in the reference's train_model) "
+                          f"in {el:.1f} s on the host; os.cpu_count()={os.cpu_count()}",
+                "ms_per_step": el / n * 1e3}, losses
 
 
 def run_reference(args):
@@ -429,14 +600,16 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    gbs = BS * world
+    wl = Workload(args.config)
+    gbs = wl.bs * world
     with all_host_threads():
-        kind, step = make_cpu_trainer(gbs)
+        kind, step = make_cpu_trainer(wl, gbs)
+        loss = None
         for _ in range(max(1, min(args.warmup, 3))):
-            step()
+            loss = step()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            step()
+            loss = step()
         el = time.perf_counter() - t0
         threads = cpu_threads()
     value = args.steps * gbs / el
@@ -446,11 +619,14 @@ def run_reference(args):
         "impl": "reference", "metric": "train_images_per_sec", "value": value, "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1] on the reference's CPU path (float64 Cython/NumPy): 32x32x3 synthetic, "
-                               "10 classes, layers [256,128,64], Adam lr 1e-4", "global_batch": gbs, "feature_dim": D},
+        "config": wl.config(world),
+        "arm_detail": {"path": "the reference's CPU path (float64 Cython/NumPy kernels, oracle/_ref) on the host cores; features "
+                               "precomputed, as in the reference's train_model; for N > 1 the global batch tiles the same rows"},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "loss_check": {"rows": f"{wl.bs} images + labels from default_rng(1000), same seeded init",
+                       "replay_steps": max(1, min(args.warmup, 3)) + args.steps, "final_loss_per_image": loss},
     }))
 
 
@@ -460,6 +636,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c1", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

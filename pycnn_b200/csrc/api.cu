@@ -773,6 +773,7 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_FUSE_SOFTMAX"); if (g && g[0] == '0') c->fuse_softmax = false; }
   { const char* g = getenv("PYCNN_B200_ONE_WAVE"); if (g && g[0] == '0') c->one_wave_tiles = false; }
   { const char* g = getenv("PYCNN_B200_PAIR"); if (g && g[0] == '0') c->use_pair = false; }
+  { const char* g = getenv("PYCNN_B200_PAIR_MIN_KB"); if (g && atoi(g) > 0) c->pair_min_kb = atoi(g); }
   { const char* g = getenv("PYCNN_B200_CLUSTER_SPLITK"); if (g && g[0] == '0') c->use_cluster_splitk = false; }
   if (c->uniform_carveout) {
     // same shared-memory carve-out as the GEMM kernels (see prepare_tc_gemm) for everything that runs beside them
@@ -1028,9 +1029,11 @@ int pycnn_b200_set_network(pycnn_b200_ctx* c, int64_t D, const int* layers, int 
   PB_TRY(alloc_f32(&c->d_m, c->P));
   PB_TRY(alloc_f32(&c->d_v, c->P));
   std::vector<Chunk> chunks;
-  const int64_t kChunk = 2048;   // one 256-thread block per chunk: >= 4 waves of blocks at 1.1 M parameters
+  // one 256-thread block per chunk: 2048 floats for the big tensors (>= 4 waves of blocks at 1.1 M parameters), short
+  // chunks for the small ones, which can collect many ordered partials (grad_finalize_kernel)
   for (size_t t = 0; t < c->tensors.size(); ++t) {
     const int64_t len = c->tensors[t].rows * c->tensors[t].ld;
+    const int64_t kChunk = len <= 300 * 1024 ? kSmallChunk : 2048;
     const int first = (int)chunks.size(), count = (int)ceil_div(len, kChunk);
     for (int64_t o = 0; o < len; o += kChunk)
       chunks.push_back({(int)t, first, count, 0, c->tensors[t].off + o, std::min(kChunk, len - o), o});

@@ -328,22 +328,61 @@ __device__ __forceinline__ double block_sum_d(double v, double* s8) {
 // One block per chunk of the flat buffer: grads[chunk] = sum_p part[p][chunk] (when the tensor has partials) and,
 // if asked, chunk_norm[chunk] = sum of squares (gradient_decent.pyx:33, np.linalg.norm per tensor -- the per-tensor
 // total is formed by the update kernel from the chunk values in chunk order).
+// Tensors that can collect many partials (biases: one per row tile; small weight matrices: up to 32 k-slices) are cut
+// into short chunks (kSmallChunk floats, set_network), and their blocks split the partials over the 8 warps: warp w
+// adds partials [w*G, (w+1)*G) in order, the 8 group sums meet in smem in warp order.  The summation tree depends only
+// on (np, chunk shape): bit-reproducible.
+constexpr int kSmallChunk = 512;   // floats
 __global__ void __launch_bounds__(256) grad_finalize_kernel(float* __restrict__ grads, const Chunk* __restrict__ chunks,
                                                             const GradParts gp, double* __restrict__ chunk_norm,
                                                             int want_norm, unsigned long long* trace) {
   __shared__ double s8[8];
+  __shared__ float4 group_sum[8][kSmallChunk / 4];
   pdl_wait();
   pdl_launch_dependents();
   trace_begin(trace);
   const Chunk ch = chunks[blockIdx.x];
   const int np = gp.nparts[ch.tensor];
   float4* g4 = reinterpret_cast<float4*>(grads + ch.off);
-  const int64_t n4 = ch.len >> 2;  // chunk offsets/lengths are multiples of 4
+  const int n4 = (int)(ch.len >> 2);  // chunk offsets/lengths are multiples of 4
   float acc = 0.f;
-  if (np > 0) {
+  if (np > 8 && n4 <= kSmallChunk / 4) {
+    const float4* p0 = reinterpret_cast<const float4*>(gp.base + gp.off[ch.tensor] + ch.rel);
+    const int64_t stride4 = gp.stride[ch.tensor] >> 2;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = (np + 7) >> 3;
+    const int pb = w * G, pe = min(np, pb + G);
+    float4 s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = pb; p < pe; p += 2) {          // 8 independent loads in flight per lane
+      float4 v[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (p + u < pe && lane + 32 * j < n4) v[u][j] = __ldcg(p0 + (int64_t)(p + u) * stride4 + lane + 32 * j);
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (p + u < pe && lane + 32 * j < n4) { s[j].x += v[u][j].x; s[j].y += v[u][j].y; s[j].z += v[u][j].z; s[j].w += v[u][j].w; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (lane + 32 * j < n4) group_sum[w][lane + 32 * j] = s[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 t = group_sum[0][i];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) { const float4 o = group_sum[k][i]; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
+      g4[i] = t;
+      acc = fmaf(t.x, t.x, acc); acc = fmaf(t.y, t.y, acc); acc = fmaf(t.z, t.z, acc); acc = fmaf(t.w, t.w, acc);
+    }
+  } else if (np > 0) {
     const float* p0 = gp.base + gp.off[ch.tensor] + ch.rel;
     const int64_t stride = gp.stride[ch.tensor];
-    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int p = 0; p < np; p += 8) {      // 8 independent loads in flight, added in index order
         float4 v[8];
@@ -358,7 +397,7 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(float* __restrict__ 
       acc = fmaf(s.x, s.x, acc); acc = fmaf(s.y, s.y, acc); acc = fmaf(s.z, s.z, acc); acc = fmaf(s.w, s.w, acc);
     }
   } else if (want_norm) {
-    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
       const float4 v = g4[i];
       acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
     }

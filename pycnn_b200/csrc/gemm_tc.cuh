@@ -700,7 +700,7 @@ static GemmPlan plan_tc_gemm(const pycnn_b200_ctx* c, const GemmCall& g) {
   // half of it and multicasts it to the pair (a third less L2->SM traffic per k-block for a 128 x 256 tile).
   const auto& occ = g_max_clusters[bn_slot(BN)][layout_slot(!g.a_kmajor, !g.b_kmajor)];
   // (measured: +30% on 500-k-block loops, nothing on 32-k-block ones, where the cluster launch costs as much as it saves)
-  const bool pair_ok = c->use_pair && tiles_m >= 2 && BN >= 64 && kb_per_split >= 64 && g.epi != 4;
+  const bool pair_ok = c->use_pair && tiles_m >= 2 && BN >= 64 && kb_per_split >= c->pair_min_kb && g.epi != 4;
   const int pair_tiles = tiles_n * (int)ceil_div(tiles_m, 2);
   bool cluster = false, pair = false;
   if (split > 1 && !g.grad_slot && c->use_cluster_splitk) {
