@@ -773,6 +773,7 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_FUSE_SOFTMAX"); if (g && g[0] == '0') c->fuse_softmax = false; }
   { const char* g = getenv("PYCNN_B200_ONE_WAVE"); if (g && g[0] == '0') c->one_wave_tiles = false; }
   { const char* g = getenv("PYCNN_B200_PAIR"); if (g && g[0] == '0') c->use_pair = false; }
+  { const char* g = getenv("PYCNN_B200_TWO_SM"); if (g && g[0] == '0') c->use_two_sm = false; }
   { const char* g = getenv("PYCNN_B200_PAIR_MIN_KB"); if (g && atoi(g) > 0) c->pair_min_kb = atoi(g); }
   { const char* g = getenv("PYCNN_B200_CLUSTER_SPLITK"); if (g && g[0] == '0') c->use_cluster_splitk = false; }
   if (c->uniform_carveout) {

@@ -143,6 +143,7 @@ struct pycnn_b200_ctx {
   bool uniform_carveout = true;        // elementwise kernels ask for the GEMMs' L1/shared split (PYCNN_B200_CARVEOUT=0 disables)
   bool fuse_softmax = true;            // training: softmax/CE/dZ in the output-layer GEMM's epilogue (PYCNN_B200_FUSE_SOFTMAX=0: own kernel)
   bool one_wave_tiles = true;          // shallow-K GEMMs: widen the tile rather than run a second wave (PYCNN_B200_ONE_WAVE=0 disables)
+  bool use_two_sm = true;              // deep 256-wide GEMM tiles run as CTA pairs on the 2-SM tensor-core path (PYCNN_B200_TWO_SM=0 disables)
   int pair_min_kb = 64;                // pairing pays from this many k-blocks per CTA on (PYCNN_B200_PAIR_MIN_KB)
   bool use_pair = true;                // M-adjacent GEMM CTAs share the B tile by TMA multicast (PYCNN_B200_PAIR=0 disables)
   bool use_cluster_splitk = true;      // split-K partials meet in distributed shared memory (PYCNN_B200_CLUSTER_SPLITK=0: global atomics)

@@ -30,10 +30,14 @@ namespace tc {
 constexpr int G_BM = 128;
 constexpr int G_BK = 32;  // floats: one 128-byte swizzle row
 
-template <int BN>
+// TWO: the CTA pair of a cluster runs as one tensor-core unit (cta_group::2): a 256 x BN tile per pair, every CTA
+// stages its own 128 rows of A and only HALF of the B tile -- 32 KB instead of 48 KB per k-block for BN = 256.  The
+// TF32 GEMMs are bound by what an SM can take in per second (~93 GB/s measured: 48 KB per 128x256x32 step is twice
+// what the tensor pipe needs time for), so the smaller stage is worth more than any multicast, which only relieves L2.
+template <int BN, bool TWO = false>
 struct GemmCfg {
   static constexpr int A_BYTES = G_BM * G_BK * 4;       // 16 KB
-  static constexpr int B_BYTES = BN * G_BK * 4;
+  static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * G_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int MAX_STAGES = (224 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
@@ -57,6 +61,7 @@ struct TcGemmArgs {
   int64_t ld_colsum;   //   output over this CTA's 128 rows -- one ordered partial per row tile, added by grad_finalize_kernel
   int cluster_reduce;  // 1: the gridDim.z k-slices of a tile share a cluster; partial tiles meet in distributed shared memory
   int pair;            // 1: two M-adjacent CTAs share a cluster; each loads half of the B tile and multicasts it to both
+                       //    (TWO kernels: always a pair -- set to 1 so that the shared cluster plumbing applies)
   // epi == 4 (output layer of a training step, N <= 32, one N tile): logits + bias -> softmax -> cross-entropy,
   // dZ = p - onehot, db_o, loss / #correct tallies and the per-step bookkeeping, all on the accumulator row a thread
   // already holds after tcgen05.ld (replaces softmax_ce_kernel; forward_pass.pyx:36-37, pycnn.py:634-640,
@@ -181,11 +186,11 @@ __device__ __forceinline__ void cluster_reduce_rows(const TcGemmArgs& g, uint8_t
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool TWO = false>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const TcGemmArgs g) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, TWO>;
   constexpr int STAGES = Cfg::STAGES;
   // 128B-swizzled TMA/UMMA tiles need a 1024-byte aligned base; declaring the alignment (instead of fixing the
   // pointer up by hand) keeps every derived pointer in the shared address space (LDS/STS, not generic LD/ST)
@@ -207,12 +212,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     prefetch_tensormap(&map_b);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], g.pair ? 2 : 1);   // paired: both CTAs' MMA issuers release a stage
+      mbar_init(&empty_bar[s], (g.pair && !TWO) ? 2 : 1);   // multicast pair: both CTAs' MMA issuers release a stage
     }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);  // BN fp32 accumulator columns (power of two >= 32)
+  if (warp == 1) {                           // BN fp32 accumulator columns (power of two >= 32)
+    if constexpr (TWO) tmem_alloc_2sm(tmem_slot, BN);
+    else tmem_alloc(tmem_slot, BN);
+  }
   fence_before_thread_sync();
   __syncthreads();
   fence_after_thread_sync();
@@ -240,8 +248,28 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         const int k0 = (kb0 + i) * G_BK;
+        if constexpr (TWO) {
+          // both CTAs of the pair fill their own stage (own A rows, own half of B) and report the bytes to the LEADER's
+          // full barrier, which the leader armed for the pair's 2 x STAGE_BYTES
+          const uint32_t lead_full = map_to_cta(smem_u32(&full_bar[s]), cluster_ctarank() & ~1u);
+          if (pair_half == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+          if (A_MN) {
+#pragma unroll
+            for (int at = 0; at < G_BM / 32; ++at) tma_load_2d_2sm(sa + at * (G_BK * 128), &map_a, lead_full, m0 + at * 32, k0);
+          } else {
+            tma_load_2d_2sm(sa, &map_a, lead_full, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int a2 = 0; a2 < BN / 64; ++a2)
+              tma_load_2d_2sm(sb + a2 * (G_BK * 128), &map_b, lead_full, n0 + ((int)pair_half * (BN / 64) + a2) * 32, k0);
+          } else {
+            tma_load_2d_2sm(sb, &map_b, lead_full, k0, n0 + (int)pair_half * (BN / 2));
+          }
+          continue;
+        }
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         if (A_MN) {
 #pragma unroll
           for (int at = 0; at < G_BM / 32; ++at) tma_load_2d(sa + at * (G_BK * 128), &map_a, &full_bar[s], m0 + at * 32, k0);
@@ -271,9 +299,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(FMT_TF32, G_BM, BN, A_MN, B_MN);
+    if (lane == 0 && (!TWO || pair_half == 0)) {
+      // ===== MMA issuer (TWO: the leader CTA issues for the pair, M = 256) =====
+      constexpr uint32_t idesc = make_idesc(FMT_TF32, TWO ? 2 * G_BM : G_BM, BN, A_MN, B_MN);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
@@ -292,14 +320,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                    : make_smem_desc(sa + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
           const uint64_t db = B_MN ? make_smem_desc(sb + k * 1024, mn_lbo, mn_sbo, UMMA_SWIZZLE_128B_BASE32B)
                                    : make_smem_desc(sb + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
-          mma_tf32(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          if constexpr (TWO) mma_tf32_2sm(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          else mma_tf32(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
         // frees this smem stage once the MMAs above have read it (in both CTAs of a pair: the peer's next
-        // multicast writes into this CTA's stage too)
-        if (g.pair) mma_commit_mc(&empty_bar[s], pair_mask);
-        else        mma_commit(&empty_bar[s]);
+        // multicast writes into this CTA's stage too / the peer's stage was read by this pair MMA)
+        if constexpr (TWO) mma_commit_2sm_mc(&empty_bar[s], pair_mask);
+        else if (g.pair) mma_commit_mc(&empty_bar[s], pair_mask);
+        else             mma_commit(&empty_bar[s]);
       }
-      mma_commit(tmem_full_bar);    // accumulator complete
+      if constexpr (TWO) mma_commit_2sm_mc(tmem_full_bar, pair_mask);   // accumulator complete, in both CTAs
+      else mma_commit(tmem_full_bar);
     }
   } else {
     // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
@@ -515,7 +546,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   trace_end(g.trace);
   if (warp == 1) {
     fence_after_thread_sync();
-    tmem_dealloc(tmem_base, BN);
+    if constexpr (TWO) tmem_dealloc_2sm(tmem_base, BN);
+    else tmem_dealloc(tmem_base, BN);
   }
 }
 
@@ -597,6 +629,30 @@ static inline int s_slot(int S) { return S == 1 ? 0 : S == 2 ? 1 : S == 4 ? 2 : 
 static inline int bn_slot(int BN) { return BN == 32 ? 0 : BN == 64 ? 1 : BN == 128 ? 2 : 3; }
 static inline int layout_slot(bool a_mn, bool b_mn) { return !a_mn ? (b_mn ? 1 : 0) : 2; }
 
+static int g_max_clusters2[3][3];   // cta_group::2 kernels (BN = 256): [layout slot][S slot: 1, 2, 4] clusters of (1, 2, S)
+
+template <bool A_MN, bool B_MN>
+static int prepare_tc_gemm_two() {
+  auto kern = tc::gemm_tf32_kernel<256, A_MN, B_MN, true>;
+  PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GemmCfg<256, true>::SMEM_BYTES));
+  PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  for (int si = 0; si < 3; ++si) {
+    const int S = 1 << si;
+    int n = 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1, 64, S);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = tc::GemmCfg<256, true>::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 2; attr[0].val.clusterDim.z = S;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+    g_max_clusters2[layout_slot(A_MN, B_MN)][si] = n;
+  }
+  return 0;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 static int prepare_tc_gemm() {
   auto kern = tc::gemm_tf32_kernel<BN, A_MN, B_MN>;
@@ -636,6 +692,9 @@ static int tc_gemm_prepare(pycnn_b200_ctx*) {
   PB_TRY((prepare_tc_gemm_bn<false, false>()));
   PB_TRY((prepare_tc_gemm_bn<false, true>()));
   PB_TRY((prepare_tc_gemm_bn<true, true>()));
+  PB_TRY((prepare_tc_gemm_two<false, false>()));
+  PB_TRY((prepare_tc_gemm_two<false, true>()));
+  PB_TRY((prepare_tc_gemm_two<true, true>()));
   return 0;
 }
 
@@ -651,7 +710,13 @@ static int launch_tc_gemm(pycnn_b200_ctx* c, const GemmCall& g, const CUtensorMa
 
 template <bool A_MN, bool B_MN>
 static int dispatch_bn(pycnn_b200_ctx* c, int BN, const GemmCall& g, const CUtensorMap& ma, const CUtensorMap& mb,
-                       const tc::TcGemmArgs& args, dim3 grid) {
+                       const tc::TcGemmArgs& args, dim3 grid, bool two) {
+  if (two) {
+    auto kern = tc::gemm_tf32_kernel<256, A_MN, B_MN, true>;
+    PB_CUDA(launch_pdl_cluster(c, kern, grid, dim3(192), (size_t)tc::GemmCfg<256, true>::SMEM_BYTES, c->stream, 2,
+                               args.cluster_reduce ? (int)grid.z : 1, ma, mb, args));
+    return 0;
+  }
   switch (BN) {
     case 32: return launch_tc_gemm<32, A_MN, B_MN>(c, g, ma, mb, args, grid);
     case 64: return launch_tc_gemm<64, A_MN, B_MN>(c, g, ma, mb, args, grid);
@@ -662,7 +727,7 @@ static int dispatch_bn(pycnn_b200_ctx* c, int BN, const GemmCall& g, const CUten
 
 struct GemmPlan {
   int BN, tiles_m, tiles_n, num_kb, split, kb_per_split;
-  bool cluster, pair;
+  bool cluster, pair, two;
 };
 
 // Tiling of one GEMM: a pure function of the shape, the call's epilogue and the context's switches (ensure_workspace
@@ -702,8 +767,17 @@ static GemmPlan plan_tc_gemm(const pycnn_b200_ctx* c, const GemmCall& g) {
   // (measured: +30% on 500-k-block loops, nothing on 32-k-block ones, where the cluster launch costs as much as it saves)
   const bool pair_ok = c->use_pair && tiles_m >= 2 && BN >= 64 && kb_per_split >= c->pair_min_kb && g.epi != 4;
   const int pair_tiles = tiles_n * (int)ceil_div(tiles_m, 2);
-  bool cluster = false, pair = false;
-  if (split > 1 && !g.grad_slot && c->use_cluster_splitk) {
+  bool cluster = false, pair = false, two = false;
+  // Deep-K 256-wide tiles with at least two M tiles run as CTA pairs on the 2-SM tensor-core path (cta_group::2).
+  // Split-K slices of such pairs meet in distributed shared memory when the (1, 2, S) clusters all fit, else they
+  // store ordered partials (gradients: the arena; anything else: the shared workspace + splitk_reduce_kernel).
+  const auto& occ2 = g_max_clusters2[layout_slot(!g.a_kmajor, !g.b_kmajor)];
+  if (c->use_two_sm && BN == 256 && tiles_m >= 2 && kb_per_split >= 8 && g.epi != 4 && !g.colsum_slot &&
+      occ2[0] >= std::min(pair_tiles * split, c->num_sms / 2)) {
+    two = true;
+    if (split > 1 && !g.grad_slot && c->use_cluster_splitk && (split == 2 || split == 4) && occ2[s_slot(split)] >= pair_tiles)
+      cluster = true;
+  } else if (split > 1 && !g.grad_slot && c->use_cluster_splitk) {
     for (int si = 3; si >= 1 && !cluster; --si) {
       const int S = 1 << si;
       if (S > split) continue;
@@ -715,7 +789,8 @@ static GemmPlan plan_tc_gemm(const pycnn_b200_ctx* c, const GemmCall& g) {
       split = S; kb_per_split = kbps;
     }
   }
-  if (!cluster && pair_ok && occ[1][0] >= std::min(pair_tiles * split, c->num_sms / 2)) pair = true;
+  if (!two && !cluster && pair_ok && occ[1][0] >= std::min(pair_tiles * split, c->num_sms / 2)) pair = true;
+  p.two = two;
   p.BN = BN; p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.num_kb = num_kb; p.split = split; p.kb_per_split = kb_per_split;
   p.cluster = cluster; p.pair = pair;
   return p;
@@ -732,16 +807,16 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   CUtensorMap ma, mb;
   if (g.a_kmajor) PB_TRY(make_map_kmajor(c, &ma, g.A, g.M, g.K, g.lda, tc::G_BM));
   else            PB_TRY(make_map_mnmajor(c, &ma, g.A, g.K, g.M, g.lda));
-  if (g.b_kmajor) PB_TRY(make_map_kmajor(c, &mb, g.B, g.N, g.K, g.ldb, p.pair ? BN / 2 : BN));
+  if (g.b_kmajor) PB_TRY(make_map_kmajor(c, &mb, g.B, g.N, g.K, g.ldb, (p.pair || p.two) ? BN / 2 : BN));
   else            PB_TRY(make_map_mnmajor(c, &mb, g.B, g.K, g.N, g.ldb));
-  dim3 grid(p.tiles_n, p.pair ? (unsigned)round_up(p.tiles_m, 2) : p.tiles_m, split);
+  dim3 grid(p.tiles_n, (p.pair || p.two) ? (unsigned)round_up(p.tiles_m, 2) : p.tiles_m, split);
   tc::TcGemmArgs a{};
   a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.N = g.N; a.K = g.K;
   a.epi = g.epi; a.partial = partial ? 1 : 0;
   a.num_kb = p.num_kb; a.kb_per_split = p.kb_per_split;
   a.bias = g.bias; a.mask = g.mask; a.ldmask = g.ldmask;
   a.cluster_reduce = p.cluster ? 1 : 0;
-  a.pair = p.pair ? 1 : 0;
+  a.pair = (p.pair || p.two) ? 1 : 0;
   a.labels = g.labels; a.dz = g.dz; a.lddz = g.lddz; a.stats = g.stats; a.bk = g.bk;
   const int64_t tile_floats = (int64_t)(g.M - 1) * g.ldc + round_up(g.N, 4);
   if (g.grad_slot) {                      // gradient tensor: ordered partials in its arena region (or C itself when unsplit)
@@ -774,9 +849,9 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   c->last_gemm_ctas = (int)(grid.x * grid.y * grid.z);
   {
     LaunchScope ls(c, g.cls);
-    if (g.a_kmajor && g.b_kmajor) PB_TRY((dispatch_bn<false, false>(c, BN, g, ma, mb, a, grid)));
-    else if (g.a_kmajor && !g.b_kmajor) PB_TRY((dispatch_bn<false, true>(c, BN, g, ma, mb, a, grid)));
-    else PB_TRY((dispatch_bn<true, true>(c, BN, g, ma, mb, a, grid)));
+    if (g.a_kmajor && g.b_kmajor) PB_TRY((dispatch_bn<false, false>(c, BN, g, ma, mb, a, grid, p.two)));
+    else if (g.a_kmajor && !g.b_kmajor) PB_TRY((dispatch_bn<false, true>(c, BN, g, ma, mb, a, grid, p.two)));
+    else PB_TRY((dispatch_bn<true, true>(c, BN, g, ma, mb, a, grid, p.two)));
   }
   if (partial && !g.grad_slot) {
     LaunchScope ls(c, g.cls);

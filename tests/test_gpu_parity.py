@@ -115,7 +115,10 @@ def test_optimized_cpp_dropins(ctx):
 # ------------------------------------------------------------------------------------------ GEMM
 GEMM_SHAPES = [(128, 256, 64), (4096 // 8, 256, 4275), (32, 10, 64), (200, 100, 1000), (256, 4275, 512), (77, 33, 45),
                (128, 64, 8), (300, 513, 96),
-               (1100, 2304, 2100)]   # deep K, odd M-tile count: paired CTAs with multicast B and a padding CTA
+               (1100, 2304, 2100),   # deep K, odd M-tile count: CTA pairs (2-SM tensor-core path) with a padding CTA
+               (2048, 256, 4275),    # layer-1 forward shape: CTA pairs x 4 k-slices through the split-K workspace
+               (256, 1030, 2048),    # layer-1 dW shape: one CTA pair per N tile, k-slices in distributed shared memory
+               (384, 300, 640)]      # three M tiles, ragged N, 20 k-blocks: pairs without split-K
 
 
 @pytest.mark.parametrize("mode,tol", [("fp32", FP32_TOL), ("tf32", 2e-3)])
