@@ -6,7 +6,10 @@ Sources are read where they lie under /root/reference (never copied into the rep
                                           -> oracle/_ref/pycnn/modules/<name>.so    (Cython -> C -> gcc)
 Flags mirror the reference's portable (CI) build: pycnn/lib/Makefile:16-17 and setup.py:200-203
 without -march=native/-ffast-math so the binaries travel to the GPU box's host CPU.
-Generated C goes to a temp dir; only .so files and empty package markers land in oracle/_ref/
+  tests/test.py                           -> oracle/_ref/tests/test.pyc             (the reference's own unittest file,
+                                             byte-compiled UNMODIFIED; tests/test_gpu_reference_own_suite.py runs it
+                                             against the drop-in on the GPU box, where /root/reference does not exist)
+Generated C goes to a temp dir; only compiled artefacts (.so, .pyc) and empty package markers land in oracle/_ref/
 (git-ignored, NOT gpurun-ignored, so it ships with the snapshot).
 
 The reference's setup.py is NOT run (it downloads wheels at import time, setup.py:94-95,190).
@@ -72,6 +75,13 @@ def build(force: bool = False, verbose: bool = True) -> bool:
             subprocess.check_call(["gcc", *cflags, "-shared", "-w",
                                    "-DNPY_NO_DEPRECATED_API=NPY_1_7_API_VERSION",
                                    *inc, "-o", dst, c_file])
+    # 3. the reference's own test file, byte-compiled (no source text enters the repo)
+    import py_compile
+    src = os.path.join(REF_ROOT, "tests", "test.py")
+    dst = os.path.join(OUT, "tests", "test.pyc")
+    if os.path.isfile(src) and (force or _newer(src, dst)):
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        py_compile.compile(src, cfile=dst, doraise=True)
     if verbose:
         print(f"[oracle.build_ref] built reference kernels into {OUT}")
     return built()
