@@ -6,7 +6,7 @@ Sources are read where they lie under /root/reference (never copied into the rep
                                           -> oracle/_ref/pycnn/modules/<name>.so    (Cython -> C -> gcc)
 Flags mirror the reference's portable (CI) build: pycnn/lib/Makefile:16-17 and setup.py:200-203
 without -march=native/-ffast-math so the binaries travel to the GPU box's host CPU.
-  tests/test.py                           -> oracle/_ref/tests/test.pyc             (the reference's own unittest file,
+  tests/test.py                           -> oracle/_ref/tests/test_py.bin            (the reference's own unittest file,
                                              byte-compiled UNMODIFIED; tests/test_gpu_reference_own_suite.py runs it
                                              against the drop-in on the GPU box, where /root/reference does not exist)
 Generated C goes to a temp dir; only compiled artefacts (.so, .pyc) and empty package markers land in oracle/_ref/
@@ -78,7 +78,7 @@ def build(force: bool = False, verbose: bool = True) -> bool:
     # 3. the reference's own test file, byte-compiled (no source text enters the repo)
     import py_compile
     src = os.path.join(REF_ROOT, "tests", "test.py")
-    dst = os.path.join(OUT, "tests", "test.pyc")
+    dst = os.path.join(OUT, "tests", "test_py.bin")     # byte code; not named .pyc: snapshot tools drop *.pyc
     if os.path.isfile(src) and (force or _newer(src, dst)):
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         py_compile.compile(src, cfile=dst, doraise=True)

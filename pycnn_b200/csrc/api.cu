@@ -73,7 +73,6 @@ int gemm(pycnn_b200_ctx* c, const GemmCall& g) {
 // ---------------------------------------------------------------------------------------------
 void free_workspace(pycnn_b200_ctx* c) {
   free_dev(c->d_gpart); c->d_gpart = nullptr; c->gpart_floats = 0;
-  free_dev(c->d_gemm_ws); c->d_gemm_ws = nullptr; c->gemm_ws_bytes = 0;
   for (auto& g : c->gp) g = GradPartSlot{};
   free_dev(c->d_blabels); c->d_blabels = nullptr;
   free_dev(c->d_x); c->d_x = nullptr;
@@ -123,10 +122,6 @@ int ensure_workspace(pycnn_b200_ctx* c, int64_t bs) {
   }
   PB_TRY(alloc_f32(&c->d_gpart, off));
   c->gpart_floats = off;
-  // shared workspace of split-K GEMMs with an epilogue whose slices cannot meet in distributed shared memory:
-  // tiles x slices never exceeds the SM count and a slice of a tile is at most 128 x 256 floats
-  c->gemm_ws_bytes = sizeof(float) * (size_t)(c->num_sms + 4) * 128 * 256;
-  PB_CUDA(cudaMalloc(&c->d_gemm_ws, c->gemm_ws_bytes));
   c->bs_cap = cap;
   return 0;
 }
@@ -429,6 +424,7 @@ int p2p_exchange_update(pycnn_b200_ctx* c) {
     t.sync[r] = static_cast<p2p::SyncBlock*>(c->p2p_peer_ptrs[2][r]);
   }
   t.rank = c->rank; t.world = c->world; t.chunk0 = c->p2p_chunk0; t.nchunks = c->p2p_nchunks;
+  t.lost = c->d_blocks_done + 2;
   const int grid = std::max(1, c->p2p_nchunks);
   {
     LaunchScope ls(c, KC_ALLREDUCE);
@@ -619,6 +615,25 @@ int zero_stats(pycnn_b200_ctx* c) {
   return 0;
 }
 
+// Data-parallel failure detection, polled wherever the host already synchronises: an asynchronous NCCL
+// error (a dead peer aborts the communicator) and the peer-memory exchange's lost-peer mark become error returns.
+int comm_health(pycnn_b200_ctx* c) {
+  if (c->world <= 1) return 0;
+  if (c->nccl_comm) {
+    NcclApi* api = nccl_api();
+    int async_err = 0;
+    if (api && api->CommGetAsyncError && api->CommGetAsyncError(c->nccl_comm, &async_err) == 0 && async_err != 0)
+      return fail("NCCL reported an asynchronous error on rank %d: %s", c->rank, api->GetErrorString ? api->GetErrorString(async_err) : "?");
+  }
+  if (c->p2p && c->d_blocks_done) {
+    unsigned int lost = 0;
+    PB_CUDA(cudaMemcpy(&lost, c->d_blocks_done + 2, sizeof(lost), cudaMemcpyDeviceToHost));
+    if (lost) return fail("peer-memory gradient exchange: rank %u did not arrive within the wait bound (seen by rank %d); "
+                          "the parameters of this step are invalid -- destroy the communicator and restart from a checkpoint", lost - 1, c->rank);
+  }
+  return 0;
+}
+
 // fixed-point loss total -> double (NaN when any contribution was non-finite, as the reference's float sum would be)
 double stats_loss(const unsigned long long* w) {
   return w[2] ? std::nan("") : (double)(long long)w[0] / kLossFixedScale;
@@ -631,6 +646,7 @@ int read_stats(pycnn_b200_ctx* c, double* loss_sum, int64_t* correct, bool allre
   }
   PB_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, kStatsWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   PB_CUDA(cudaStreamSynchronize(c->stream));
+  PB_TRY(comm_health(c));
   if (loss_sum) *loss_sum = stats_loss(c->h_stats);
   if (correct) *correct = (int64_t)c->h_stats[1];
   return 0;
@@ -758,6 +774,10 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   CREATE_CUDA(cudaMalloc(&c->d_stats, kStatsWords * sizeof(unsigned long long)));
   CREATE_CUDA(cudaMemset(c->d_stats, 0, kStatsWords * sizeof(unsigned long long)));
   CREATE_CUDA(cudaMallocHost(&c->h_stats, kStatsWords * sizeof(unsigned long long)));
+  // shared workspace of split-K GEMMs with an epilogue whose slices cannot meet in distributed shared memory:
+  // tiles x slices never exceeds the SM count and a slice of a tile is at most 128 x 256 floats
+  c->gemm_ws_bytes = sizeof(float) * (size_t)(c->num_sms + 4) * 128 * 256;
+  CREATE_CUDA(cudaMalloc(&c->d_gemm_ws, c->gemm_ws_bytes));
   CREATE_CUDA(cudaMalloc(&c->d_cursor, 2 * sizeof(int64_t)));
   CREATE_CUDA(cudaMemset(c->d_cursor, 0, 2 * sizeof(int64_t)));
 #undef CREATE_CUDA
@@ -1682,8 +1702,8 @@ int pycnn_b200_comm_ipc_export(pycnn_b200_ctx* c, char* blob) {
   PB_CUDA(cudaMalloc(&c->p2p_sync, sizeof(p2p::SyncBlock)));
   PB_CUDA(cudaMemset(c->p2p_sync, 0, sizeof(p2p::SyncBlock)));
   PB_CUDA(cudaMalloc(&c->d_p2p_seq, 2 * sizeof(long long)));
-  PB_CUDA(cudaMalloc(&c->d_blocks_done, 2 * sizeof(unsigned int)));
-  PB_CUDA(cudaMemset(c->d_blocks_done, 0, 2 * sizeof(unsigned int)));
+  PB_CUDA(cudaMalloc(&c->d_blocks_done, 4 * sizeof(unsigned int)));      // [0], [1] block counters, [2] lost-peer mark
+  PB_CUDA(cudaMemset(c->d_blocks_done, 0, 4 * sizeof(unsigned int)));
   const long long init[2] = {0, 0};
   PB_CUDA(cudaMemcpy(c->d_p2p_seq, init, sizeof(init), cudaMemcpyHostToDevice));
   cudaIpcMemHandle_t h[3];

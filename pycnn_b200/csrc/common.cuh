@@ -324,10 +324,11 @@ __device__ __forceinline__ void trace_mark(unsigned long long* slot, int phase) 
 }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// launch as thread-block clusters of (1, cluster_y, cluster_z) when that is more than one CTA
+// launch as thread-block clusters of (cluster_x, cluster_y, cluster_z) when that is more than one CTA
 template <class... KArgs, class... Args>
-static inline cudaError_t launch_pdl_cluster(pycnn_b200_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block,
-                                             size_t smem, cudaStream_t stream, int cluster_y, int cluster_z, Args&&... args) {
+static inline cudaError_t launch_pdl_cluster3(pycnn_b200_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                                              size_t smem, cudaStream_t stream, int cluster_x, int cluster_y, int cluster_z,
+                                              Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -340,14 +341,19 @@ static inline cudaError_t launch_pdl_cluster(pycnn_b200_ctx* c, void (*kernel)(K
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (cluster_y * cluster_z > 1) {
+  if (cluster_x * cluster_y * cluster_z > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = (unsigned)cluster_y; attr[na].val.clusterDim.z = (unsigned)cluster_z;
+    attr[na].val.clusterDim.x = (unsigned)cluster_x; attr[na].val.clusterDim.y = (unsigned)cluster_y; attr[na].val.clusterDim.z = (unsigned)cluster_z;
     ++na;
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl_cluster(pycnn_b200_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                                             size_t smem, cudaStream_t stream, int cluster_y, int cluster_z, Args&&... args) {
+  return launch_pdl_cluster3(c, kernel, grid, block, smem, stream, 1, cluster_y, cluster_z, static_cast<Args&&>(args)...);
 }
 
 template <class... KArgs, class... Args>

@@ -489,24 +489,38 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ pa
     u.inv_bc1 = (float)(1.0 / (1.0 - pow(u.beta1_d, t)));
     u.inv_bc2 = (float)(1.0 / (1.0 - pow(u.beta2_d, t)));
   }
+  // a chunk is at most 2048 floats = two 128-bit elements per thread: all of the thread's operands are requested
+  // BEFORE the tensor norm is formed, so the HBM round trip of p, g, m, v overlaps the norm's L2 round trip + reduction
+  const int n4 = (int)(ch.len >> 2);
+  float4* p4 = reinterpret_cast<float4*>(params + ch.off);
+  const float4* g4 = reinterpret_cast<const float4*>(grads + ch.off);
+  float4* m4 = reinterpret_cast<float4*>(m + ch.off);
+  float4* v4 = reinterpret_cast<float4*>(v + ch.off);
+  float4 p[2], g[2], mm[2], vv[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int i = threadIdx.x + e * 256;
+    mm[e] = vv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) {
+      p[e] = p4[i]; g[e] = __ldcg(g4 + i);
+      if (u.opt == 1) { mm[e] = m4[i]; vv[e] = v4[i]; }
+    }
+  }
   if (u.rule == 0) {
     const double n2 = tensor_norm2(chunk_norm, ch, s8);
     if (!isfinite(n2)) return;  // NaN/Inf gradient: skip this tensor's update
     const double nrm = sqrt(n2);
     if (nrm > (double)u.max_norm) scale = (float)((double)u.max_norm / nrm);
   }
-  const int64_t n4 = ch.len >> 2;
-  float4* p4 = reinterpret_cast<float4*>(params + ch.off);
-  const float4* g4 = reinterpret_cast<const float4*>(grads + ch.off);
-  float4* m4 = reinterpret_cast<float4*>(m + ch.off);
-  float4* v4 = reinterpret_cast<float4*>(v + ch.off);
   const float omb1 = 1.0f - u.beta1, omb2 = 1.0f - u.beta2;
-  for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
-    float4 p = p4[i], mm = make_float4(0.f, 0.f, 0.f, 0.f), vv = mm;
-    if (u.opt == 1) { mm = m4[i]; vv = v4[i]; }
-    adam_or_sgd4(p, mm, vv, g4[i], scale, u, omb1, omb2);
-    p4[i] = p;
-    if (u.opt == 1) { m4[i] = mm; v4[i] = vv; }
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int i = threadIdx.x + e * 256;
+    if (i < n4) {
+      adam_or_sgd4(p[e], mm[e], vv[e], g[e], scale, u, omb1, omb2);
+      p4[i] = p[e];
+      if (u.opt == 1) { m4[i] = mm[e]; v4[i] = vv[e]; }
+    }
   }
   trace_end(trace);
 }
@@ -542,23 +556,40 @@ __global__ void f32_padded_to_f32_kernel(const float* __restrict__ src, int64_t 
   }
 }
 
-// split-K without atomics (fallback when the k-slices cannot meet in distributed shared memory): out = epilogue(sum of the
-// S partial tiles in slice order).  epi: 0 none, 1 +bias, 2 relu(+bias), 3 mask by (act > 0)
-__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int S, int64_t part_stride, float* __restrict__ c,
-                                     int M, int N, int64_t ldc, int epi, const float* __restrict__ bias,
-                                     const float* __restrict__ mask, int64_t ldmask) {
+// split-K without atomics (k-slices that cannot meet in distributed shared memory): out = epilogue(sum of the S raw
+// partial tiles in slice order).  epi: 0 none, 1 +bias, 2 relu(+bias), 3 mask by (act > 0).  128-bit accesses: ldc and
+// part_stride are multiples of 4 and the partial rows carry exact zeros in their padding columns.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int S, int64_t part_stride,
+                                                            float* __restrict__ c, int M, int N, int64_t ldc, int epi,
+                                                            const float* __restrict__ bias,
+                                                            const float* __restrict__ mask, int64_t ldmask) {
   pdl_wait();
   pdl_launch_dependents();
-  const int64_t total = (int64_t)M * N;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / N, n = i - r * N;
-    float v = 0.f;
-    for (int z = 0; z < S; ++z) v += __ldcg(ws + (int64_t)z * part_stride + r * ldc + n);
-    if (epi == 1 || epi == 2) v += bias[n];
-    if (epi == 2) v = (v < 0.f) ? 0.f : v;
-    if (epi == 3) v = (mask[r * ldmask + n] <= 0.f) ? 0.f : v;
-    c[r * ldc + n] = v;
+  const int n4 = (N + 3) >> 2;
+  const int64_t total = (int64_t)M * n4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / n4;
+    const int n = (int)(i - r * n4) * 4;
+    const float* p0 = ws + r * ldc + n;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < S; z += 4) {          // 4 independent loads in flight, added in slice order
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (z + u < S) t[u] = __ldcg(reinterpret_cast<const float4*>(p0 + (int64_t)(z + u) * part_stride));
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (z + u < S) { v.x += t[u].x; v.y += t[u].y; v.z += t[u].z; v.w += t[u].w; }
+    }
+    float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (n + e >= N) { o[e] = 0.f; continue; }
+      if (epi == 1 || epi == 2) o[e] += __ldg(bias + n + e);
+      if (epi == 2) o[e] = (o[e] < 0.f) ? 0.f : o[e];
+      if (epi == 3) o[e] = (__ldg(mask + r * ldmask + n + e) <= 0.f) ? 0.f : o[e];
+    }
+    *reinterpret_cast<float4*>(c + r * ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 

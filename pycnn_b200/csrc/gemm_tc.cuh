@@ -39,7 +39,9 @@ struct GemmCfg {
   static constexpr int A_BYTES = G_BM * G_BK * 4;       // 16 KB
   static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * G_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int MAX_STAGES = (224 * 1024) / STAGE_BYTES;
+  // <= 208 KB of stages: clustered launches of a CTA that asks for more than ~200 KB of dynamic shared memory are
+  // refused on this part ("cluster misconfiguration", seen at 225 KB), and 6 x 32 KB stages are deep enough
+  static constexpr int MAX_STAGES = (208 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -78,6 +80,8 @@ struct TcGemmArgs {
 // ---- thread-block cluster helpers (split-K reduction through distributed shared memory) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_ctaid_x() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctaid_x() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_ctaid_y() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctaid.y;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_ctaid_z() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctaid.z;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctaid_y() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctaid.y;" : "=r"(r)); return r; }
@@ -103,15 +107,16 @@ __device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
 // Cluster split-K tail (see the kernel): CTA `rank` of S finishes rows [rank*128/S, (rank+1)*128/S) of the tile.  A warp
 // takes RG rows at a time so that RG*S = 16 remote 128-bit loads are in flight per lane (DSMEM latency is ~2x L2's).
 template <int BN, int S>
-__device__ __forceinline__ void cluster_reduce_rows(const TcGemmArgs& g, uint8_t* smem, int q, int lane, int m0, int n0) {
+__device__ __forceinline__ void cluster_reduce_rows(const TcGemmArgs& g, uint8_t* smem, int q, int lane, int m0, int n0,
+                                                    uint32_t P, uint32_t py) {
   constexpr int PITCH = BN + 4;
   constexpr int RPC = G_BM / S;        // rows per CTA: 64 / 32 / 16
   constexpr int RPW = RPC / 4;         // rows per warp: 16 / 8 / 4
   constexpr int RG = 16 / S;           // rows per batch: 8 / 4 / 2
   constexpr int PASSES = (BN + 127) / 128;
-  // cluster shape (1, P, S), P = 2 when M-adjacent CTAs pair up for the B multicast: %cluster_ctarank = y + P*z
+  // cluster shape (1, P, S) -- or (P, 1, S) for the 2-SM kernels -- with P = 2 when M-adjacent CTAs pair up:
+  // %cluster_ctarank = (pair index py) + P*z
   const uint32_t rank = cluster_ctaid_z();
-  const uint32_t P = cluster_nctaid_y(), py = cluster_ctaid_y();
   const int ncols = min(BN, g.N - n0);
   const uint32_t stage_local = smem_u32(smem);
   uint32_t stage_of[S];
@@ -202,7 +207,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * G_BM;
+  // grid: (N tiles, M tiles, k-slices); the 2-SM kernels put the M tiles on x, because the two CTAs of a cta_group::2
+  // pair must be neighbours in the cluster's x dimension (a (1,2,1) cluster is refused at launch)
+  const int tile_n = TWO ? blockIdx.y : blockIdx.x, tile_m = TWO ? blockIdx.x : blockIdx.y;
+  const int n0 = tile_n * BN, m0 = tile_m * G_BM;
   const int kb0 = blockIdx.z * g.kb_per_split;
   const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
   const int nkb = kb1 - kb0;  // host guarantees >= 1
@@ -232,7 +240,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     cluster_sync_all();
     const uint32_t r = cluster_ctarank();
     pair_mask = (uint16_t)(3u << (r & ~1u));
-    pair_half = cluster_ctaid_y();
+    pair_half = TWO ? cluster_ctaid_x() : cluster_ctaid_y();
   }
   // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
   pdl_wait();
@@ -348,7 +356,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if constexpr (BN == 32 && !A_MN && !B_MN) {
       if (g.epi == 4) {
         fused_softmax = true;
-        if (blockIdx.x == 0 && blockIdx.y == 0 && q == 0 && lane == 0) step_bookkeeping(g.bk);   // per-step housekeeping
+        if (tile_n == 0 && tile_m == 0 && q == 0 && lane == 0) step_bookkeeping(g.bk);   // per-step housekeeping
         float v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), v);
         const int C = g.N;
@@ -402,7 +410,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
         if (q == 0 && lane < (int)g.lddz) {
           const float tot = (lane < C) ? ((cs_smem[lane] + cs_smem[32 + lane]) + (cs_smem[64 + lane] + cs_smem[96 + lane])) : 0.f;
-          g.db_part[(int64_t)blockIdx.y * g.lddz + lane] = tot;
+          g.db_part[(int64_t)tile_m * g.lddz + lane] = tot;
         }
       }
     }
@@ -418,8 +426,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
     __syncwarp();
-    if (!g.cluster_reduce) {
-    float* const Cout = g.C + (g.partial ? (int64_t)blockIdx.z * g.part_stride : 0);
+    if (g.partial && !g.cluster_reduce) {
+      // raw partial tile of a k-slice: every lane hands its staged row to the bulk-copy engine (one 1-D TMA store of
+      // up to 1 KB per row) instead of walking it through registers -- the epilogue is then the TMEM drain alone
+      float* const Cout = g.C + (int64_t)blockIdx.z * g.part_stride;
+      const int64_t row = (int64_t)m0 + q * 32 + lane;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (row < g.M) bulk_store(Cout + row * g.ldc + n0, stage + lane * PITCH, (uint32_t)(((ncols + 3) & ~3) * 4));
+      bulk_commit();
+      bulk_wait_read<0>();
+    } else if (!g.cluster_reduce) {
+    float* const Cout = g.C;
     const int row0 = m0 + q * 32;
     const int nrows = min(32, g.M - row0);            // warp-uniform, may be <= 0
     const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
@@ -514,7 +532,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const float* cs_all = reinterpret_cast<const float*>(smem) + 128 * PITCH;
       for (int j = (warp - 2) * 32 + lane; j < ncols; j += 128) {
         const float tot = (cs_all[j] + cs_all[BN + j]) + (cs_all[2 * BN + j] + cs_all[3 * BN + j]);
-        if (n0 + j < g.N) g.colsum_part[(int64_t)blockIdx.y * g.ld_colsum + n0 + j] = tot;
+        if (n0 + j < g.N) g.colsum_part[(int64_t)tile_m * g.ld_colsum + n0 + j] = tot;
       }
     }
     }  // !cluster_reduce
@@ -531,10 +549,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // smem -- measured 2.4 us slower: it needs one more cluster barrier before anyone may overwrite operand smem.)
     cluster_sync_all();
     if (warp >= 2) {
+      const uint32_t P = TWO ? cluster_nctaid_x() : cluster_nctaid_y(), py = TWO ? cluster_ctaid_x() : cluster_ctaid_y();
       switch (cluster_nctaid_z()) {
-        case 2: cluster_reduce_rows<BN, 2>(g, smem, warp & 3, lane, m0, n0); break;
-        case 4: cluster_reduce_rows<BN, 4>(g, smem, warp & 3, lane, m0, n0); break;
-        default: cluster_reduce_rows<BN, 8>(g, smem, warp & 3, lane, m0, n0); break;
+        case 2: cluster_reduce_rows<BN, 2>(g, smem, warp & 3, lane, m0, n0, P, py); break;
+        case 4: cluster_reduce_rows<BN, 4>(g, smem, warp & 3, lane, m0, n0, P, py); break;
+        default: cluster_reduce_rows<BN, 8>(g, smem, warp & 3, lane, m0, n0, P, py); break;
       }
     }
     cluster_sync_all();
@@ -629,7 +648,7 @@ static inline int s_slot(int S) { return S == 1 ? 0 : S == 2 ? 1 : S == 4 ? 2 : 
 static inline int bn_slot(int BN) { return BN == 32 ? 0 : BN == 64 ? 1 : BN == 128 ? 2 : 3; }
 static inline int layout_slot(bool a_mn, bool b_mn) { return !a_mn ? (b_mn ? 1 : 0) : 2; }
 
-static int g_max_clusters2[3][3];   // cta_group::2 kernels (BN = 256): [layout slot][S slot: 1, 2, 4] clusters of (1, 2, S)
+static int g_max_clusters2[3][3];   // cta_group::2 kernels (BN = 256): [layout slot][S slot: 1, 2, 4] clusters of (2, 1, S)
 
 template <bool A_MN, bool B_MN>
 static int prepare_tc_gemm_two() {
@@ -640,12 +659,12 @@ static int prepare_tc_gemm_two() {
     const int S = 1 << si;
     int n = 0;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(1, 64, S);
+    cfg.gridDim = dim3(64, 1, S);
     cfg.blockDim = dim3(192);
     cfg.dynamicSmemBytes = tc::GemmCfg<256, true>::SMEM_BYTES;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 2; attr[0].val.clusterDim.z = S;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
     g_max_clusters2[layout_slot(A_MN, B_MN)][si] = n;
@@ -713,8 +732,9 @@ static int dispatch_bn(pycnn_b200_ctx* c, int BN, const GemmCall& g, const CUten
                        const tc::TcGemmArgs& args, dim3 grid, bool two) {
   if (two) {
     auto kern = tc::gemm_tf32_kernel<256, A_MN, B_MN, true>;
-    PB_CUDA(launch_pdl_cluster(c, kern, grid, dim3(192), (size_t)tc::GemmCfg<256, true>::SMEM_BYTES, c->stream, 2,
-                               args.cluster_reduce ? (int)grid.z : 1, ma, mb, args));
+    // M tiles on x: the CTAs of a cta_group::2 pair must be neighbours in the cluster's x dimension
+    PB_CUDA(launch_pdl_cluster3(c, kern, dim3(grid.y, grid.x, grid.z), dim3(192), (size_t)tc::GemmCfg<256, true>::SMEM_BYTES,
+                                c->stream, 2, 1, args.cluster_reduce ? (int)grid.z : 1, ma, mb, args));
     return 0;
   }
   switch (BN) {
@@ -855,7 +875,7 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   }
   if (partial && !g.grad_slot) {
     LaunchScope ls(c, g.cls);
-    const int64_t total = (int64_t)g.M * g.N;
+    const int64_t total = (int64_t)g.M * ceil_div(g.N, 4);
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 8 * c->num_sms);
     PB_CUDA(launch_pdl(c, splitk_reduce_kernel, dim3(blocks), dim3(256), 0, c->stream, (const float*)c->d_gemm_ws, split,
                        a.part_stride, g.C, g.M, g.N, g.ldc, g.epi, g.bias, g.mask, g.ldmask));

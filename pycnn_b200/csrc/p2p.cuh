@@ -19,7 +19,7 @@
 //                          rank's parameters are complete.                                        (all-gather)
 //
 // Flags are monotonically increasing step sequence numbers written with st.release.sys / read with
-// ld.acquire.sys; all spins are bounded (trap, never hang).  Every rank runs the same two launches every
+// ld.acquire.sys; all spins are bounded (a lost peer is recorded and reported by the host, never a hang or a trap).  Every rank runs the same two launches every
 // step (also with an empty shard), each on its own GPU.
 #pragma once
 #include "elementwise.cuh"
@@ -44,6 +44,7 @@ struct PeerTable {
   SyncBlock* sync[MAX_RANKS];
   int rank, world;
   int chunk0, nchunks;                    // owned chunk range of the flat buffer
+  unsigned int* lost;                     // local word: 0, or 1 + rank of a peer whose flag never arrived (host reports it)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -59,13 +60,17 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// bounded spin on a flag a peer writes into MY memory: relaxed polls (cheap), one acquire once it flipped;
-// ~2^26 polls (seconds) and a lost peer traps instead of hanging the GPU
-__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long seq) {
+// bounded spin on a flag a peer writes into MY memory: relaxed polls (cheap), one acquire once it flipped.  A peer that
+// never arrives (crashed rank, lost link) must not hang the GPU and must not kill the context either: after ~2^25 polls
+// (seconds) the waiter records 1 + the peer's rank in *lost and carries on -- every later wait of this launch and of
+// the following ones sees the mark and returns at once, the step's numbers are garbage, and the host raises a clean
+// error ("rank r did not arrive") when it reads the epoch's totals (read_stats).
+__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long seq, unsigned int* lost, int peer) {
   unsigned int polls = 0;
   while (ld_relaxed_sys(p) < seq) {
     if (++polls > 256u) __nanosleep(20);
-    if (polls > (1u << 26)) __trap();
+    if ((polls & 1023u) == 0u && *reinterpret_cast<volatile unsigned int*>(lost) != 0u) return;
+    if (polls > (1u << 25)) { atomicCAS(lost, 0u, (unsigned int)peer + 1u); return; }
   }
   (void)ld_acquire_sys(p);
 }
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chun
     __threadfence_system();   // my backward pass (previous kernels of this stream) is visible system-wide
     st_release_sys(&t.sync[threadIdx.x]->grads_ready[t.rank], seq);
   }
-  if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->grads_ready[threadIdx.x], seq);
+  if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->grads_ready[threadIdx.x], seq, t.lost, threadIdx.x);
   __syncthreads();
   __shared__ double sh[8];
   if ((int)blockIdx.x < t.nchunks) {
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(256) p2p_update_kernel(PeerTable t, const Chun
     float scale = 1.0f;
     bool skip = false;
     if (u.rule == 0) {   // norms of the fully reduced gradient: every rank's partials, summed in rank order
-      if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->norms_ready[threadIdx.x], seq);
+      if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->norms_ready[threadIdx.x], seq, t.lost, threadIdx.x);
       __syncthreads();
       if (threadIdx.x == 0) {
         double n2 = 0.0;
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__(256) p2p_update_kernel(PeerTable t, const Chun
   if (last) {
     if (threadIdx.x == 0) *blocks_done = 0u;
     if (threadIdx.x < t.world) st_release_sys(&t.sync[threadIdx.x]->params_done[t.rank], seq);
-    if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->params_done[threadIdx.x], seq);
+    if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->params_done[threadIdx.x], seq, t.lost, threadIdx.x);
     __syncthreads();
     if (threadIdx.x == 0) seq_ptr[1] = (long long)seq;   // every block of this launch has already read the old value
   }

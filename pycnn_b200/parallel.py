@@ -103,6 +103,56 @@ def allreduce_scalars(values, op="sum"):
     return t.cpu().tolist()
 
 
+def gather_shards(local, n_total, rank, world):
+    """Concatenate per-rank result arrays of an image-sharded job (image_shard order) on every rank.  Host-side:
+    the data path itself has no collective, this only brings the (small) per-image results together."""
+    if world == 1:
+        return local
+    import torch.distributed as dist
+    parts = [None] * world
+    dist.all_gather_object(parts, np.ascontiguousarray(local))
+    out = np.concatenate([p for p in parts if len(p)]) if n_total else np.asarray(local)
+    assert len(out) == n_total, (len(out), n_total)
+    return out
+
+
+def predict_sharded(ctx, images, rank, world):
+    """Batched predict over `world` GPUs: every rank runs the fused extractor + forward on its contiguous N/W image
+    range (pycnn/pycnn.py:737-773 per image; no collective), results are gathered on every rank.
+    -> (classes int32 [N], confidences float32 [N])"""
+    n = len(images)
+    lo, hi = image_shard(n, rank, world)
+    if hi > lo:
+        cls, conf = ctx.predict_images(np.ascontiguousarray(images[lo:hi]))
+    else:
+        cls, conf = np.zeros(0, np.int32), np.zeros(0, np.float32)
+    return gather_shards(cls, n, rank, world), gather_shards(conf, n, rank, world)
+
+
+def evaluate_sharded(ctx, images, labels, batch_size, rank, world):
+    """Evaluate._run_inference (pycnn/pycnn.py:873-914) over `world` GPUs: each rank evaluates its image range in
+    chunks of batch_size; loss sums and correct counts are added on the host, predictions gathered.
+    -> (loss_sum, correct, predicted int32 [N])"""
+    n = len(images)
+    lo, hi = image_shard(n, rank, world)
+    if hi > lo:
+        loss, correct, pred = ctx.evaluate_images(np.ascontiguousarray(images[lo:hi]),
+                                                  np.ascontiguousarray(labels[lo:hi], dtype=np.int32), batch_size)
+    else:
+        loss, correct, pred = 0.0, 0, np.zeros(0, np.int32)
+    loss, correct = allreduce_scalars([loss, float(correct)])
+    return loss, int(round(correct)), gather_shards(pred, n, rank, world)
+
+
+def extract_sharded(ctx, images, rank, world, row0=0):
+    """Feature extraction over `world` GPUs: rank r extracts ITS image range into rows [row0, row0 + hi - lo) of its own
+    device dataset (dataset_alloc first); features stay where they were produced.  -> (lo, hi)"""
+    lo, hi = image_shard(len(images), rank, world)
+    if hi > lo:
+        ctx.dataset_extract(row0, np.ascontiguousarray(images[lo:hi]))
+    return lo, hi
+
+
 class ShardedStepper:
     """Reference implementation of the sharded step with a pluggable compute + all-reduce, used by the
     world_size-2 gloo tests to pin the host logic (slice arithmetic, sum-not-mean reduction, identical

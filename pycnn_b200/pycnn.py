@@ -653,9 +653,14 @@ class PyCNN:
         return self.classes[int(cls[0])], float(conf[0])
 
     def predict_batch(self, images):
-        """Extension: batched predict on uint8 [n,S,S,3] -> (class indices, confidences)."""
+        """Extension: batched predict on uint8 [n,S,S,3] -> (class indices, confidences).  Under torchrun (after
+        parallel.attach) the images are sharded over the ranks' GPUs -- no collective in the data path -- and every
+        rank returns the full result (a collective call: every rank passes the same images)."""
         ctx = self._push_params()
         self._sync_filters(self.filters)
+        if self._world > 1:
+            from . import parallel
+            return parallel.predict_sharded(ctx, np.asarray(images), self._rank, self._world)
         return ctx.predict_images(images)
 
 
@@ -765,7 +770,15 @@ class Evaluate:
         m._sync_filters(m.filters)
         n = len(images)
         bs = getattr(m, "batch_size", 32)
-        loss_sum, correct, pred = ctx.evaluate_images(np.stack(images), np.asarray(label_idx, dtype=np.int32), bs)
+        if m._world > 1:       # image-sharded over the ranks' GPUs: tallies are added on the host
+            from . import parallel
+            loss_sum, correct, pred = parallel.evaluate_sharded(ctx, np.stack(images), np.asarray(label_idx, dtype=np.int32),
+                                                                bs, m._rank, m._world)
+            if m._rank != 0:
+                self.last_result = {"acc": correct / n, "loss": loss_sum / n}
+                return
+        else:
+            loss_sum, correct, pred = ctx.evaluate_images(np.stack(images), np.asarray(label_idx, dtype=np.int32), bs)
         print(f"\rEvaluating: {n}/{n}", end="", flush=True)
         self._report(loss_sum, correct, pred, np.asarray(label_idx))
 

@@ -1,6 +1,6 @@
 """`from pycnn.pycnn import PyCNN, Evaluate` -- what a user who switches the reference's `cuda(True)` on gets when
 pycnn_b200 is dropped in.  The reference's own unittest file (tests/test.py, compiled unmodified into
-oracle/_ref/tests/test.pyc by oracle/build_ref.py) never calls cuda(); this subclass turns the backend on the first
+oracle/_ref/tests/test_py.bin by oracle/build_ref.py) never calls cuda(); this subclass turns the backend on the first
 time a compute path needs it, exactly as if `model.cuda(True)` had been the user's first call.  Nothing else is
 overridden: every assertion of that file runs against libpycnn_b200.so."""
 import contextlib

@@ -1,6 +1,6 @@
 """The reference's OWN unittest file (tests/test.py:9-223, 16 cases) run UNMODIFIED against the drop-in.
 
-oracle/build_ref.py byte-compiles /root/reference/tests/test.py into oracle/_ref/tests/test.pyc (git-ignored, travels
+oracle/build_ref.py byte-compiles /root/reference/tests/test.py into oracle/_ref/tests/test_py.bin (git-ignored, travels
 to the GPU box; no reference source text enters the repo).  Here that module is loaded under a `pycnn` package that
 resolves to pycnn_b200 with the B200 backend switched on (tests/ref_shim), and all 16 cases must pass: API shape,
 defaults, dataset loading, the max-pool known answer, save/load round trip, training, prediction, evaluation."""
@@ -15,10 +15,10 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PYC = os.path.join(ROOT, "oracle", "_ref", "tests", "test.pyc")
+PYC = os.path.join(ROOT, "oracle", "_ref", "tests", "test_py.bin")
 
 
-@pytest.mark.skipif(not os.path.isfile(PYC), reason="oracle/_ref/tests/test.pyc not built (python -m oracle.build_ref)")
+@pytest.mark.skipif(not os.path.isfile(PYC), reason="oracle/_ref/tests/test_py.bin not built (python -m oracle.build_ref)")
 def test_reference_unittest_file_passes_against_the_drop_in(capsys):
     shim = os.path.join(ROOT, "tests", "ref_shim")
     saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "pycnn" or k.startswith("pycnn.")}
