@@ -60,10 +60,12 @@ print(f"# {steps} steps in {ms * 1e3:.1f} us = {ms * 1e3 / steps:.2f} us/step (C
 # a step starts at a layer-1 forward GEMM on the main stream
 ev_sorted = sorted(ev, key=lambda e: e[2])
 starts_t = sorted(e[2] for e in ev if e[0] == "gemm_forward_layer1")
-if len(starts_t) >= 3:
+if len(starts_t) >= 1:
     k = len(starts_t) // 2
-    t0, t1 = starts_t[k], starts_t[k + 1]
-    print(f"# step {k}: {(t1 - t0) / 1e3:.2f} us from its layer-1 GEMM start to the next one's")
+    # (single-step graphs reuse their slots at every replay: only the last step is there)
+    t0, t1 = (starts_t[k], starts_t[k + 1]) if len(starts_t) >= 3 else (starts_t[-1], 1 << 62)
+    if len(starts_t) >= 3:
+        print(f"# step {k}: {(t1 - t0) / 1e3:.2f} us from its layer-1 GEMM start to the next one's")
     print(f"{'kernel':24s} {'stream':>6s} {'start us':>9s} {'end us':>9s} {'dur us':>8s}   GEMM phase marks, us after the kernel's first CTA start (min..max over CTAs)")
     for name, sid, a, b, *marks in ev_sorted:
         if t0 <= a < t1:
