@@ -8,6 +8,7 @@
 #include "gemm_tc.cuh"
 #include "p2p.cuh"
 #include "simt.cuh"
+#include "tail_fused.cuh"
 
 using namespace pb;
 
@@ -244,9 +245,11 @@ bool softmax_fusable(const pycnn_b200_ctx* c) {
 // x: [bs, Dp].  Leaves hidden activations in d_act and logits in d_probs (pitch ldw[L+1]).
 // train_labels != nullptr (only with softmax_fusable): the last GEMM runs the fused softmax/CE epilogue instead of
 // writing logits -- dZ_out lands in d_dz[L], loss/#correct in d_stats, db_o as ordered partials (one per row tile).
-int forward_logits(pycnn_b200_ctx* c, const float* x, int bs, const int32_t* train_labels = nullptr, int64_t advance = 0) {
+int forward_logits(pycnn_b200_ctx* c, const float* x, int bs, const int32_t* train_labels = nullptr, int64_t advance = 0,
+                   int last_layer = -1) {
   const float* in = x;
-  for (int l = 0; l <= c->L; ++l) {
+  if (last_layer < 0) last_layer = c->L;
+  for (int l = 0; l <= last_layer; ++l) {
     GemmCall g{};
     g.A = in; g.lda = c->ldw[l]; g.a_kmajor = true;
     g.B = c->d_params + Wt(c, l).off; g.ldb = Wt(c, l).ld; g.b_kmajor = true;
@@ -290,6 +293,95 @@ int softmax_ce(pycnn_b200_ctx* c, int bs, const int32_t* labels, bool write_prob
                      c->ldw[c->L + 1], labels, write_probs ? c->d_probs : (float*)nullptr,
                      write_dz ? c->d_dz[c->L] : (float*)nullptr, write_pred ? c->d_pred : (int32_t*)nullptr,
                      write_pred ? c->d_conf : (float*)nullptr, stats ? c->d_stats : (unsigned long long*)nullptr, db_part, bk));
+  return 0;
+}
+
+// ---- fused tail (tail_fused.cuh): forward layers 2..L+1, softmax/CE and the whole dA chain in one launch -------------
+bool tail_eligible(const pycnn_b200_ctx* c) {
+  if (!c->use_tail || c->math_mode != PYCNN_B200_MATH_TF32 || !c->fuse_softmax) return false;
+  if (c->L < 1 || 2 * c->L > tail::MAX_STAGES || c->C > 32 || c->dims[1] > tail::MAX_IN) return false;
+  for (int l = 2; l <= c->L; ++l)
+    if (c->dims[l] > tail::MAX_MID) return false;
+  return true;
+}
+
+// a1 = relu(z1 + b1) is in d_act[0].  Leaves a2..aL in d_act, dZ_{L+1}..dZ_1 in d_dz, loss/#correct in d_stats and the
+// bias gradients of every layer as ordered partials (one per 128-row tile).
+int tail_forward_backward(pycnn_b200_ctx* c, int bs, const int32_t* labels, int64_t advance) {
+  const int L = c->L, tiles = (int)ceil_div(bs, 128);
+  tail::TailArgs t{};
+  t.bs = bs; t.nstages = 2 * L;
+  t.a_in = c->d_act[0]; t.ld_in = c->ldw[1]; t.in_width = (int)c->dims[1];
+  t.labels = labels; t.stats = c->d_stats;
+  t.bk = StepBookkeeping{c->d_cursor, advance};
+  CUtensorMap maps[1 + tail::MAX_STAGES];
+  PB_TRY(make_map_kmajor(c, &maps[0], c->d_act[0], bs, c->dims[1], c->ldw[1], 128));
+  auto bias_part = [&](int layer, float** part, int64_t* ld) -> int {      // ordered partial slot of b_layer (0-based layer)
+    GradPartSlot& gs = c->gp[2 * layer + 1];
+    PB_CHECK(tiles <= gs.cap, "bias-gradient partial arena too small (%d row tiles, cap %d)", tiles, gs.cap);
+    gs.nparts = tiles;
+    *part = c->d_gpart + gs.off; *ld = gs.stride;
+    return 0;
+  };
+  int s = 0;
+  for (int l = 1; l <= L; ++l, ++s) {            // forward: network layer l (0-based) = hidden layers 2..L, then the output layer
+    tail::Stage& S = t.st[s];
+    const TensorDesc& w = Wt(c, l);
+    S.K = (int)c->dims[l]; S.N = (int)c->dims[l + 1]; S.b_mn = 0;
+    S.bias = c->d_params + Bt(c, l).off;
+    if (l < L) { S.epi = 0; S.mask_slot = l; S.out = c->d_act[l]; S.ld_out = c->ldw[l + 1]; }
+    else       { S.epi = 1; S.out = c->d_dz[L]; S.ld_out = c->ldw[L + 1]; PB_TRY(bias_part(L, &S.colsum_part, &S.ld_colsum)); }
+    PB_TRY(make_map_kmajor(c, &maps[1 + s], c->d_params + w.off, w.rows, w.cols, w.ld, (int)round_up(std::min<int64_t>(w.rows, 128), 16)));
+  }
+  for (int l = L; l >= 1; --l, ++s) {            // backward: dZ_{l-1} = (dZ_l . W_l) masked by a_{l-1} > 0   (0-based l)
+    tail::Stage& S = t.st[s];
+    const TensorDesc& w = Wt(c, l);
+    S.K = (int)c->dims[l + 1]; S.N = (int)c->dims[l]; S.b_mn = 1; S.epi = 2; S.mask_slot = l - 1;
+    S.out = c->d_dz[l - 1]; S.ld_out = c->ldw[l];
+    PB_TRY(bias_part(l - 1, &S.colsum_part, &S.ld_colsum));
+    PB_TRY(make_map_mnmajor(c, &maps[1 + s], c->d_params + w.off, w.rows, w.cols, w.ld));
+  }
+  for (; s < tail::MAX_STAGES; ++s) maps[1 + s] = maps[1];
+  t.trace = trace_slot(c, KC_GEMM_FWD);
+  LaunchScope ls(c, KC_GEMM_FWD);
+  PB_CUDA(launch_pdl(c, tail::tail_fused_kernel, dim3((unsigned)tiles), dim3(tail::THREADS), (size_t)tail::SMEM_BYTES, c->stream,
+                     maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], maps[8], t));
+  return 0;
+}
+
+// dW GEMMs after the fused tail: dW of layers 2..L+1 need only what the tail kernel left in memory, so they all run on
+// the side stream, capped to the SMs dW of layer 1 (main stream, the critical path) leaves idle.
+int backward_dw_after_tail(pycnn_b200_ctx* c, const float* x, int bs) {
+  const bool fork = !c->timing && c->side_stream != nullptr;
+  cudaStream_t main_stream = c->stream;
+  auto dw_call = [&](int l) {
+    GemmCall g{};
+    g.A = c->d_dz[l]; g.lda = c->ldw[l + 1]; g.a_kmajor = false;
+    g.B = (l == 0) ? x : c->d_act[l - 1]; g.ldb = c->ldw[l]; g.b_kmajor = false;
+    g.C = c->d_grads + Wt(c, l).off; g.ldc = Wt(c, l).ld;
+    g.M = (int)c->dims[l + 1]; g.N = (int)c->dims[l]; g.K = bs; g.epi = 0; g.cls = (l == 0) ? KC_GEMM_DW1 : KC_GEMM_DW;
+    g.grad_slot = 2 * l + 1;
+    return g;
+  };
+  if (fork) PB_CUDA(cudaEventRecord(c->ev_fork[0], main_stream));
+  PB_TRY(gemm(c, dw_call(0)));
+  const int room = c->num_sms - c->last_gemm_ctas;
+  if (fork) {
+    PB_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork[0], 0));
+    c->stream = c->side_stream;
+  }
+  int rc = 0;
+  for (int l = c->L; l >= 1 && !rc; --l) {
+    GemmCall g = dw_call(l);
+    if (fork && room >= 8) g.max_ctas = room;
+    rc = gemm(c, g);
+  }
+  c->stream = main_stream;
+  PB_TRY(rc);
+  if (fork) {
+    PB_CUDA(cudaEventRecord(c->ev_join, c->side_stream));
+    PB_CUDA(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
+  }
   return 0;
 }
 
@@ -482,14 +574,19 @@ int join_prefetch(pycnn_b200_ctx* c) {
 int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int bs, bool update, int64_t advance = 0) {
   begin_grads(c);
   if (bs > 0) {
-    if (softmax_fusable(c)) {
+    if (tail_eligible(c)) {
+      PB_TRY(forward_logits(c, x, bs, nullptr, 0, 0));          // layer 1 only (+ the row-gather prefetch fork)
+      PB_TRY(tail_forward_backward(c, bs, labels, advance));
+      PB_TRY(backward_dw_after_tail(c, x, bs));
+    } else if (softmax_fusable(c)) {
       PB_TRY(forward_logits(c, x, bs, labels, advance));
+      PB_TRY(backward(c, x, bs));
     } else {
       PB_TRY(forward_logits(c, x, bs));
       // probs are not written during training; dZ goes to its own buffer
       PB_TRY(softmax_ce(c, bs, labels, false, true, false, true, true, advance));
+      PB_TRY(backward(c, x, bs));
     }
-    PB_TRY(backward(c, x, bs));
   } else {   // empty shard on this rank: contribute zero gradients, still advance the cursor
     PB_TRY(zero_grads(c));
     LaunchScope ls(c, KC_MISC);
@@ -793,6 +890,11 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_FUSE_SOFTMAX"); if (g && g[0] == '0') c->fuse_softmax = false; }
   { const char* g = getenv("PYCNN_B200_ONE_WAVE"); if (g && g[0] == '0') c->one_wave_tiles = false; }
   { const char* g = getenv("PYCNN_B200_PAIR"); if (g && g[0] == '0') c->use_pair = false; }
+  { const char* g = getenv("PYCNN_B200_NVTX"); if (g && g[0] == '1') c->nvtx = true; }
+  { const char* g = getenv("PYCNN_B200_FUSED_TAIL"); if (g && g[0] == '0') c->use_tail = false; }
+  { cudaError_t e = cudaFuncSetAttribute(tail::tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail::tail_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) { fail("cudaFuncSetAttribute(tail_fused_kernel) failed: %s", cudaGetErrorString(e)); return bail(1); } }
   { const char* g = getenv("PYCNN_B200_TWO_SM"); if (g && g[0] == '0') c->use_two_sm = false; }
   { const char* g = getenv("PYCNN_B200_PAIR_MIN_KB"); if (g && atoi(g) > 0) c->pair_min_kb = atoi(g); }
   { const char* g = getenv("PYCNN_B200_CLUSTER_SPLITK"); if (g && g[0] == '0') c->use_cluster_splitk = false; }

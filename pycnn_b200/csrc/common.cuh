@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler injects itself
 
 #include <cmath>
 #include <cstdarg>
@@ -143,6 +144,8 @@ struct pycnn_b200_ctx {
   bool uniform_carveout = true;        // elementwise kernels ask for the GEMMs' L1/shared split (PYCNN_B200_CARVEOUT=0 disables)
   bool fuse_softmax = true;            // training: softmax/CE/dZ in the output-layer GEMM's epilogue (PYCNN_B200_FUSE_SOFTMAX=0: own kernel)
   bool one_wave_tiles = true;          // shallow-K GEMMs: widen the tile rather than run a second wave (PYCNN_B200_ONE_WAVE=0 disables)
+  bool nvtx = false;                   // NVTX range per kernel class around every launch / capture (PYCNN_B200_NVTX=1)
+  bool use_tail = true;                // forward layers 2.. + softmax + the dA chain as one kernel (tail_fused.cuh; PYCNN_B200_FUSED_TAIL=0 disables)
   bool use_two_sm = true;              // deep 256-wide GEMM tiles run as CTA pairs on the 2-SM tensor-core path (PYCNN_B200_TWO_SM=0 disables)
   int pair_min_kb = 64;                // pairing pays from this many k-blocks per CTA on (PYCNN_B200_PAIR_MIN_KB)
   bool use_pair = true;                // M-adjacent GEMM CTAs share the B tile by TMA multicast (PYCNN_B200_PAIR=0 disables)
@@ -274,6 +277,7 @@ struct LaunchScope {
   LaunchScope(pycnn_b200_ctx* ctx, int k, int n_launches = 1) : c(ctx), cls(k) {
     c->launches += n_launches;
     c->class_launches[cls] += n_launches;
+    if (c->nvtx) nvtxRangePushA(kKernelClassNames[cls]);      // one range per kernel class (PYCNN_B200_NVTX=1)
     if (c->timing) {
       a = take();
       b = take();
@@ -281,6 +285,7 @@ struct LaunchScope {
     }
   }
   ~LaunchScope() {
+    if (c->nvtx) nvtxRangePop();
     if (c->timing) {
       cudaEventRecord(b, c->stream);
       c->timed[cls].push_back({a, b});

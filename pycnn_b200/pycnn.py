@@ -15,8 +15,10 @@ NumPy compute path and no CPU fallback.  What differs from the reference, on pur
 """
 from __future__ import annotations
 
+import json
 import os
 import pickle
+import time
 
 import numpy as np
 
@@ -499,9 +501,18 @@ class PyCNN:
         self._resumed = False
         plot = _LivePlot(self.epochs) if visualize else None
         best_loss, stop_counter, patience = float("inf"), 0, early_stop
+        perf_log = os.environ.get("PYCNN_B200_PERF_LOG") if self._rank == 0 else None   # one JSON line per epoch
         for epoch in range(int(start_epoch), self.epochs):
             perm = np.random.permutation(num_samples)                     # :622, host stream
+            t_epoch, launches0 = time.perf_counter(), ctx.launch_count()
             loss_sum, correct = ctx.train_epoch(perm, self.batch_size)    # :626-642 in one call
+            if perf_log:
+                dt = time.perf_counter() - t_epoch
+                with open(perf_log, "a") as f:
+                    f.write(json.dumps({"epoch": epoch + 1, "seconds": dt, "images_per_s": num_samples / dt, "images": num_samples,
+                                        "batch_size": self.batch_size, "loss": loss_sum / max(1, num_samples),
+                                        "acc": correct / max(1, num_samples), "gpu_launches": ctx.launch_count() - launches0,
+                                        "world": self._world}) + "\n")
             epoch_loss = loss_sum / max(1, num_samples)
             epoch_acc = correct / max(1, num_samples)
             if early_stop:

@@ -37,6 +37,8 @@ def make_model(images, labels, attach, epochs=EPOCHS):
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("PYCNN_B200_WORKER_DEADLINE", "240")), exit=True)   # a stuck collective shows WHERE
     rank, world, local = parallel.init_process_group("nccl")
     images, labels = synth_images(N, S, 31), synth_labels(N, C, 32)
 

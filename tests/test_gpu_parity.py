@@ -623,7 +623,8 @@ def _epoch_run(lib, env, monkeypatch, mode, opt, n=2100, bs=128, epochs=2, S=32,
     """`epochs` epochs over n rows (short last batch) in a fresh context created under `env`; returns per-epoch
     (loss, correct) and the final parameters."""
     for k in ("PYCNN_B200_PREFETCH", "PYCNN_B200_GRAPH_STEPS", "PYCNN_B200_FUSE_SOFTMAX", "PYCNN_B200_CLUSTER_SPLITK",
-              "PYCNN_B200_FORK", "PYCNN_B200_PDL", "PYCNN_B200_GRAPHS", "PYCNN_B200_CARVEOUT", "PYCNN_B200_DEFER_DW"):
+              "PYCNN_B200_FORK", "PYCNN_B200_PDL", "PYCNN_B200_GRAPHS", "PYCNN_B200_CARVEOUT", "PYCNN_B200_DEFER_DW",
+              "PYCNN_B200_FUSED_TAIL", "PYCNN_B200_TWO_SM"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -693,11 +694,13 @@ def test_training_is_bit_reproducible(lib, monkeypatch, mode, opt):
         np.testing.assert_array_equal(x, y)
 
 
-@pytest.mark.parametrize("env", [{"PYCNN_B200_FUSE_SOFTMAX": "0"}, {"PYCNN_B200_CLUSTER_SPLITK": "0"}],
-                         ids=["softmax_kernel", "workspace_splitk"])
+@pytest.mark.parametrize("env", [{"PYCNN_B200_FUSE_SOFTMAX": "0"}, {"PYCNN_B200_CLUSTER_SPLITK": "0"}, {"PYCNN_B200_FUSED_TAIL": "0"},
+                                 {"PYCNN_B200_TWO_SM": "0"}],
+                         ids=["softmax_kernel", "workspace_splitk", "per_layer_tail", "one_sm_gemm"])
 def test_fused_epilogues_match_separate_kernels(lib, monkeypatch, env):
     """TF32 path: softmax/CE in the output-layer GEMM epilogue vs softmax_ce_kernel, cluster (DSMEM) split-K vs the
-    workspace + ordered-reduce fallback -- same losses and parameters up to TF32 / summation-order noise."""
+    workspace + ordered-reduce fallback, the fused tail kernel vs one GEMM launch per layer, CTA-pair (2-SM) GEMMs vs
+    single-CTA ones -- same losses and parameters up to TF32 / summation-order noise."""
     base_stats, base_params = _epoch_run(lib, {}, monkeypatch, "tf32", "sgd", layers=(256, 64))
     stats, params = _epoch_run(lib, env, monkeypatch, "tf32", "sgd", layers=(256, 64))
     for (l0, c0), (l1, c1) in zip(base_stats, stats):

@@ -206,6 +206,57 @@ def test_world2_gloo_sharded_training_equals_single_process(tmp_path):
     assert "GLOO_OK" in res.stdout
 
 
+_SHARD_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, {root!r})
+import torch.distributed as dist
+from pycnn_b200 import parallel
+
+class FakeCtx:
+    # stands in for the CUDA context: "predicts" a deterministic function of the pixels so that any mix-up of
+    # shard order or a dropped / duplicated image shows in the gathered result
+    def predict_images(self, images):
+        s = images.reshape(len(images), -1).astype(np.int64).sum(1)
+        return (s % 7).astype(np.int32), (s % 100 / 100.0).astype(np.float32)
+    def evaluate_images(self, images, labels, bs):
+        cls, _ = self.predict_images(images)
+        return float((cls + 1).sum()), int((cls == labels).sum()), cls
+
+rank, world, _ = parallel.init_process_group("gloo")
+rng = np.random.default_rng(5)
+for n in (0 + 5, 64, 1001):                   # fewer images than ranks x 4, even, ragged
+    images = rng.integers(0, 256, (n, 4, 4, 3), dtype=np.uint8)
+    labels = rng.integers(0, 7, n).astype(np.int32)
+    want_cls, want_conf = FakeCtx().predict_images(images)
+    cls, conf = parallel.predict_sharded(FakeCtx(), images, rank, world)
+    assert np.array_equal(cls, want_cls) and np.array_equal(conf, want_conf), n
+    loss, correct, pred = parallel.evaluate_sharded(FakeCtx(), images, labels, 32, rank, world)
+    assert np.array_equal(pred, want_cls) and correct == int((want_cls == labels).sum()) and loss == float((want_cls + 1).sum()), n
+    lo, hi = parallel.image_shard(n, rank, world)
+    spans = [None] * world
+    dist.all_gather_object(spans, (lo, hi))
+    assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+print("SHARD_OK", rank)
+dist.destroy_process_group()
+"""
+
+
+def test_world2_gloo_image_sharded_predict_and_evaluate(tmp_path):
+    """Extraction / predict / Evaluate shard per image with no collective in the data path: the host logic
+    (contiguous N/W ranges, host-side gather and tally sums) on two gloo ranks with a stand-in context."""
+    script = tmp_path / "shard_worker.py"
+    script.write_text(_SHARD_WORKER.format(root=ROOT))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert res.stdout.count("SHARD_OK") == 2
+
+
 def test_checkpoint_sidecar_does_not_shadow_model_bin(tmp_path):
     """the resumable checkpoint is a separate, tagged file; a reference-format model.bin is refused by
     load_checkpoint before any device work (so this runs without a GPU) and the tag is what save_checkpoint writes."""
