@@ -38,6 +38,20 @@ int grid_for(int64_t total, int threads, int num_sms) {
 // ---------------------------------------------------------------------------------------------
 // GEMM dispatch: TF32 tensor cores by default, FP32 SIMT in verification mode
 // ---------------------------------------------------------------------------------------------
+// bias gradient db = column sums of dz [M, N] as ordered partials (one per row chunk) in tensor `slot`'s arena region
+int colsum_partials(pycnn_b200_ctx* c, const float* dz, int M, int N, int64_t ld, int slot) {
+  GradPartSlot& gs = c->gp[slot];
+  const int col_blocks = (int)ceil_div(N, 32);
+  const int chunks = std::max(1, std::min({(int)ceil_div(M, 64), (2 * c->num_sms + col_blocks - 1) / col_blocks, gs.cap}));
+  const int rows_per_block = (int)ceil_div(M, chunks);
+  dim3 cgrid((unsigned)col_blocks, (unsigned)ceil_div(M, rows_per_block));
+  PB_CHECK((int)cgrid.y <= gs.cap, "bias-gradient partial arena too small (%d row chunks, cap %d)", (int)cgrid.y, gs.cap);
+  gs.nparts = (int)cgrid.y;
+  LaunchScope ls(c, KC_COLSUM);
+  PB_CUDA(launch_pdl(c, colsum_kernel, cgrid, dim3(32, 8), 0, c->stream, dz, M, N, ld, c->d_gpart + gs.off, gs.stride, rows_per_block));
+  return 0;
+}
+
 int gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   if (g.M <= 0 || g.N <= 0) return 0;
   if (c->math_mode == PYCNN_B200_MATH_TF32) return tc_gemm(c, g);
@@ -54,18 +68,7 @@ int gemm(pycnn_b200_ctx* c, const GemmCall& g) {
     PB_CUDA(cudaGetLastError());
   }
   if (g.grad_slot) c->gp[g.grad_slot - 1].nparts = 0;   // unsplit: C is the flat gradient buffer itself
-  if (g.colsum_slot) {   // the tensor-core kernel fuses this into its epilogue
-    GradPartSlot& gs = c->gp[g.colsum_slot - 1];
-    const int col_blocks = (int)ceil_div(g.N, 32);
-    const int chunks = std::max(1, std::min({(int)ceil_div(g.M, 64), (2 * c->num_sms + col_blocks - 1) / col_blocks, gs.cap}));
-    const int rows_per_block = (int)ceil_div(g.M, chunks);
-    dim3 cgrid((unsigned)col_blocks, (unsigned)ceil_div(g.M, rows_per_block));
-    PB_CHECK((int)cgrid.y <= gs.cap, "bias-gradient partial arena too small (%d row chunks, cap %d)", (int)cgrid.y, gs.cap);
-    gs.nparts = (int)cgrid.y;
-    LaunchScope ls(c, KC_COLSUM);
-    colsum_kernel<<<cgrid, dim3(32, 8), 0, c->stream>>>(g.C, g.M, g.N, g.ldc, c->d_gpart + gs.off, gs.stride, rows_per_block);
-    PB_CUDA(cudaGetLastError());
-  }
+  if (g.colsum_slot) PB_TRY(colsum_partials(c, g.C, g.M, g.N, g.ldc, g.colsum_slot - 1));   // the tensor-core kernel fuses this
   return 0;
 }
 
@@ -254,6 +257,9 @@ int forward_logits(pycnn_b200_ctx* c, const float* x, int bs, const int32_t* tra
     g.A = in; g.lda = c->ldw[l]; g.a_kmajor = true;
     g.B = c->d_params + Wt(c, l).off; g.ldb = Wt(c, l).ld; g.b_kmajor = true;
     g.M = bs; g.N = (int)c->dims[l + 1]; g.K = (int)c->dims[l];
+    if (l == 0 && c->gsrc.on) {            // gather-free: the batch is rows idx[cursor ...) of the dataset
+      g.A = c->d_feat; g.gather_idx = c->d_idx; g.gather_cursor = c->d_cursor; g.gather_extra = 0; g.gather_rows = c->n_rows;
+    }
     g.bias = c->d_params + Bt(c, l).off;
     g.cls = (l == 0) ? KC_GEMM_FWD1 : KC_GEMM_FWD;
     if (l < c->L) { g.C = c->d_act[l]; g.epi = 2; }
@@ -265,8 +271,9 @@ int forward_logits(pycnn_b200_ctx* c, const float* x, int bs, const int32_t* tra
       g.db_slot = 2 * c->L + 2;
       g.bk = StepBookkeeping{c->d_cursor, advance};
     }
+    if (l == 0 && c->pf_early) PB_TRY(issue_prefetch(c));   // no-op unless a pipelined training step armed it
     PB_TRY(gemm(c, g));
-    if (l == 0) PB_TRY(issue_prefetch(c));   // no-op unless a pipelined training step armed it
+    if (l == 0) PB_TRY(issue_prefetch(c));
     in = g.C;
   }
   return 0;
@@ -306,16 +313,9 @@ bool tail_eligible(const pycnn_b200_ctx* c) {
 }
 
 // a1 = relu(z1 + b1) is in d_act[0].  Leaves a2..aL in d_act, dZ_{L+1}..dZ_1 in d_dz, loss/#correct in d_stats and the
-// bias gradients of every layer as ordered partials (one per 128-row tile).
+// every dZ_l in d_dz, and the bias gradients of every layer as ordered partials (one per 128-row tile).
 int tail_forward_backward(pycnn_b200_ctx* c, int bs, const int32_t* labels, int64_t advance) {
   const int L = c->L, tiles = (int)ceil_div(bs, 128);
-  tail::TailArgs t{};
-  t.bs = bs; t.nstages = 2 * L;
-  t.a_in = c->d_act[0]; t.ld_in = c->ldw[1]; t.in_width = (int)c->dims[1];
-  t.labels = labels; t.stats = c->d_stats;
-  t.bk = StepBookkeeping{c->d_cursor, advance};
-  CUtensorMap maps[1 + tail::MAX_STAGES];
-  PB_TRY(make_map_kmajor(c, &maps[0], c->d_act[0], bs, c->dims[1], c->ldw[1], 128));
   auto bias_part = [&](int layer, float** part, int64_t* ld) -> int {      // ordered partial slot of b_layer (0-based layer)
     GradPartSlot& gs = c->gp[2 * layer + 1];
     PB_CHECK(tiles <= gs.cap, "bias-gradient partial arena too small (%d row tiles, cap %d)", tiles, gs.cap);
@@ -323,6 +323,13 @@ int tail_forward_backward(pycnn_b200_ctx* c, int bs, const int32_t* labels, int6
     *part = c->d_gpart + gs.off; *ld = gs.stride;
     return 0;
   };
+  tail::TailArgs t{};
+  t.bs = bs; t.nstages = 2 * L;
+  t.a_in = c->d_act[0]; t.ld_in = c->ldw[1]; t.in_width = (int)c->dims[1];
+  t.labels = labels; t.stats = c->d_stats;
+  t.bk = StepBookkeeping{c->d_cursor, advance};
+  tail::TailMaps tm;
+  PB_TRY(make_map_kmajor(c, &tm.in, c->d_act[0], bs, c->dims[1], c->ldw[1], 128));
   int s = 0;
   for (int l = 1; l <= L; ++l, ++s) {            // forward: network layer l (0-based) = hidden layers 2..L, then the output layer
     tail::Stage& S = t.st[s];
@@ -331,7 +338,8 @@ int tail_forward_backward(pycnn_b200_ctx* c, int bs, const int32_t* labels, int6
     S.bias = c->d_params + Bt(c, l).off;
     if (l < L) { S.epi = 0; S.mask_slot = l; S.out = c->d_act[l]; S.ld_out = c->ldw[l + 1]; }
     else       { S.epi = 1; S.out = c->d_dz[L]; S.ld_out = c->ldw[L + 1]; PB_TRY(bias_part(L, &S.colsum_part, &S.ld_colsum)); }
-    PB_TRY(make_map_kmajor(c, &maps[1 + s], c->d_params + w.off, w.rows, w.cols, w.ld, (int)round_up(std::min<int64_t>(w.rows, 128), 16)));
+    PB_TRY(make_map_kmajor(c, &tm.b[s], c->d_params + w.off, w.rows, w.cols, w.ld, (int)round_up(std::min<int64_t>(w.rows, 128), 16)));
+    PB_TRY(make_map_kmajor(c, &tm.o[s], S.out, bs, S.N, S.ld_out, 128));     // the stage's output tile leaves by TMA store
   }
   for (int l = L; l >= 1; --l, ++s) {            // backward: dZ_{l-1} = (dZ_l . W_l) masked by a_{l-1} > 0   (0-based l)
     tail::Stage& S = t.st[s];
@@ -339,13 +347,14 @@ int tail_forward_backward(pycnn_b200_ctx* c, int bs, const int32_t* labels, int6
     S.K = (int)c->dims[l + 1]; S.N = (int)c->dims[l]; S.b_mn = 1; S.epi = 2; S.mask_slot = l - 1;
     S.out = c->d_dz[l - 1]; S.ld_out = c->ldw[l];
     PB_TRY(bias_part(l - 1, &S.colsum_part, &S.ld_colsum));
-    PB_TRY(make_map_mnmajor(c, &maps[1 + s], c->d_params + w.off, w.rows, w.cols, w.ld));
+    PB_TRY(make_map_mnmajor(c, &tm.b[s], c->d_params + w.off, w.rows, w.cols, w.ld));
+    PB_TRY(make_map_kmajor(c, &tm.o[s], S.out, bs, S.N, S.ld_out, 128));
   }
-  for (; s < tail::MAX_STAGES; ++s) maps[1 + s] = maps[1];
+  for (; s < tail::MAX_STAGES; ++s) { tm.b[s] = tm.b[0]; tm.o[s] = tm.o[0]; }
   t.trace = trace_slot(c, KC_GEMM_FWD);
   LaunchScope ls(c, KC_GEMM_FWD);
   PB_CUDA(launch_pdl(c, tail::tail_fused_kernel, dim3((unsigned)tiles), dim3(tail::THREADS), (size_t)tail::SMEM_BYTES, c->stream,
-                     maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], maps[8], t));
+                     tm, t));
   return 0;
 }
 
@@ -361,6 +370,9 @@ int backward_dw_after_tail(pycnn_b200_ctx* c, const float* x, int bs) {
     g.C = c->d_grads + Wt(c, l).off; g.ldc = Wt(c, l).ld;
     g.M = (int)c->dims[l + 1]; g.N = (int)c->dims[l]; g.K = bs; g.epi = 0; g.cls = (l == 0) ? KC_GEMM_DW1 : KC_GEMM_DW;
     g.grad_slot = 2 * l + 1;
+    if (l == 0 && c->gsrc.on) {            // the step's bookkeeping has already moved the cursor past this batch
+      g.B = c->d_feat; g.gather_idx = c->d_idx; g.gather_cursor = c->d_cursor; g.gather_extra = -c->gsrc.advance; g.gather_rows = c->n_rows;
+    }
     return g;
   };
   if (fork) PB_CUDA(cudaEventRecord(c->ev_fork[0], main_stream));
@@ -409,6 +421,9 @@ int backward(pycnn_b200_ctx* c, const float* x, int bs) {
       g.C = c->d_grads + Wt(c, l).off; g.ldc = Wt(c, l).ld;
       g.M = out_n; g.N = in_n; g.K = bs; g.epi = 0; g.cls = (l == 0) ? KC_GEMM_DW1 : KC_GEMM_DW;
       g.grad_slot = 2 * l + 1;
+      if (l == 0 && c->gsrc.on) {
+        g.B = c->d_feat; g.gather_idx = c->d_idx; g.gather_cursor = c->d_cursor; g.gather_extra = -c->gsrc.advance; g.gather_rows = c->n_rows;
+      }
       if (defer && l == 1) {
         deferred = g; have_deferred = true;      // launched below, behind dW of layer 1
       } else if (fork && l > 0) {
@@ -576,12 +591,15 @@ int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int 
   if (bs > 0) {
     if (tail_eligible(c)) {
       PB_TRY(forward_logits(c, x, bs, nullptr, 0, 0));          // layer 1 only (+ the row-gather prefetch fork)
+      if (c->gsrc.on) PB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_pf_join, 0));     // the batch labels (side stream)
       PB_TRY(tail_forward_backward(c, bs, labels, advance));
       PB_TRY(backward_dw_after_tail(c, x, bs));
     } else if (softmax_fusable(c)) {
+      if (c->gsrc.on) PB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_pf_join, 0));
       PB_TRY(forward_logits(c, x, bs, labels, advance));
       PB_TRY(backward(c, x, bs));
     } else {
+      if (c->gsrc.on) PB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_pf_join, 0));
       PB_TRY(forward_logits(c, x, bs));
       // probs are not written during training; dZ goes to its own buffer
       PB_TRY(softmax_ce(c, bs, labels, false, true, false, true, true, advance));
@@ -665,7 +683,7 @@ int run_graphed(pycnn_b200_ctx* c, std::tuple<int, int64_t, int64_t, int64_t, in
   return 0;
 }
 
-enum GraphKind { GK_STEP_ROWS = 1, GK_STEP_IMAGES = 2, GK_STEP_ROWS_PF = 3 };
+enum GraphKind { GK_STEP_ROWS = 1, GK_STEP_IMAGES = 2, GK_STEP_ROWS_PF = 3, GK_STEP_ROWS_GF = 8 };
 
 // one training step on dataset rows d_idx[*cursor + lo .. +bs), then cursor += advance
 int graphed_step_rows(pycnn_b200_ctx* c, int bs, int64_t lo, int64_t advance) {
@@ -699,6 +717,41 @@ int graphed_step_rows_pf(pycnn_b200_ctx* c, int bs, int next_bs, int parity, int
       if (rc || rj) return rc ? rc : rj;
     }
     return 0;
+  });
+}
+
+// Gather-free steps (the default for batches large enough for the 2-SM layer-1 GEMMs): `count` consecutive steps of bs
+// rows in one graph.  No batch buffer, no gather kernel, no prefetch stream: the layer-1 GEMMs fetch rows
+// idx[cursor ...) of the dataset themselves (TMA gather4), only the bs labels are gathered -- on the side stream, beside
+// the layer-1 forward GEMM.  The step's bookkeeping moves the cursor on by bs.
+bool gather_free_ok(pycnn_b200_ctx* c, int bs) {
+  if (!c->use_gather_free || c->math_mode != PYCNN_B200_MATH_TF32 || bs <= 0 || !c->side_stream) return false;
+  GemmCall f{};
+  f.a_kmajor = true; f.b_kmajor = true; f.M = bs; f.N = (int)c->dims[1]; f.K = (int)c->dims[0]; f.epi = 2;
+  GemmCall w{};
+  w.a_kmajor = false; w.b_kmajor = false; w.M = (int)c->dims[1]; w.N = (int)c->dims[0]; w.K = bs; w.grad_slot = 1;
+  return gather_ok(c, f) && gather_ok(c, w);
+}
+
+int graphed_step_rows_gf(pycnn_b200_ctx* c, int bs, int count) {
+  return run_graphed(c, std::make_tuple((int)GK_STEP_ROWS_GF, (int64_t)bs, (int64_t)count, (int64_t)0, 0), [&]() -> int {
+    int rc = 0;
+    for (int j = 0; j < count && !rc; ++j) {
+      // labels of this batch: side stream, joined before the first kernel that reads them
+      PB_CUDA(cudaEventRecord(c->ev_pf_fork, c->stream));
+      PB_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_pf_fork, 0));
+      {
+        LaunchScope ls(c, KC_GATHER);
+        gather_labels_kernel<<<(unsigned)std::min<int64_t>(ceil_div(bs, 256), 64), 256, 0, c->side_stream>>>(
+            c->d_labels, c->d_idx, c->d_cursor, bs, c->d_blabels);
+        PB_CUDA(cudaGetLastError());
+      }
+      PB_CUDA(cudaEventRecord(c->ev_pf_join, c->side_stream));
+      c->gsrc.on = true; c->gsrc.advance = bs;
+      rc = step_on_batch(c, nullptr, c->d_blabels, bs, true, bs);
+      c->gsrc.on = false;
+    }
+    return rc;
   });
 }
 
@@ -887,9 +940,11 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_GRAPH_STEPS"); if (g && atoi(g) > 0) c->graph_steps = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PF_CTAS"); if (g && atoi(g) > 0) c->pf_ctas_per_sm = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PREFETCH"); if (g && g[0] == '0') c->use_prefetch = false; }
+  { const char* g = getenv("PYCNN_B200_PF_EARLY"); if (g) c->pf_early = (g[0] == '1'); }
   { const char* g = getenv("PYCNN_B200_FUSE_SOFTMAX"); if (g && g[0] == '0') c->fuse_softmax = false; }
   { const char* g = getenv("PYCNN_B200_ONE_WAVE"); if (g && g[0] == '0') c->one_wave_tiles = false; }
   { const char* g = getenv("PYCNN_B200_PAIR"); if (g && g[0] == '0') c->use_pair = false; }
+  { const char* g = getenv("PYCNN_B200_GATHER_FREE"); if (g) c->use_gather_free = (g[0] == '1'); }
   { const char* g = getenv("PYCNN_B200_NVTX"); if (g && g[0] == '1') c->nvtx = true; }
   { const char* g = getenv("PYCNN_B200_FUSED_TAIL"); if (g && g[0] == '0') c->use_tail = false; }
   { cudaError_t e = cudaFuncSetAttribute(tail::tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES);
@@ -1333,7 +1388,8 @@ int pycnn_b200_train_step(pycnn_b200_ctx* c, const int64_t* idx, int bs, double*
   PB_CUDA(cudaMemcpyAsync(c->d_idx, idx, sizeof(int64_t) * bs, cudaMemcpyHostToDevice, c->stream));
   PB_TRY(zero_stats(c));
   PB_TRY(reset_cursor(c));
-  PB_TRY(graphed_step_rows(c, bs, 0, bs));
+  if (gather_free_ok(c, bs)) PB_TRY(graphed_step_rows_gf(c, bs, 1));
+  else                       PB_TRY(graphed_step_rows(c, bs, 0, bs));
   if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += 1;
   if (loss_sum || correct) PB_TRY(read_stats(c, loss_sum, correct, true));
   return 0;
@@ -1349,7 +1405,14 @@ int pycnn_b200_train_steps(pycnn_b200_ctx* c, const int64_t* idx, int bs, int st
   PB_CUDA(cudaMemcpyAsync(c->d_idx, idx, sizeof(int64_t) * bs * steps, cudaMemcpyHostToDevice, c->stream));
   PB_TRY(zero_stats(c));
   PB_TRY(reset_cursor(c));
-  if (c->use_prefetch && steps > 1) {
+  if (gather_free_ok(c, bs)) {
+    for (int s = 0; s < steps;) {
+      int count = 1;
+      while (2 * count <= c->graph_steps && s + 2 * count <= steps) count *= 2;
+      PB_TRY(graphed_step_rows_gf(c, bs, count));
+      s += count;
+    }
+  } else if (c->use_prefetch && steps > 1) {
     PB_TRY(ensure_prefetch_buffers(c));
     PB_TRY(prime_rows(c, bs));
     for (int s = 0; s < steps;) {   // greedy 16/8/4/2/1-step graphs, as in train_epoch
@@ -1401,7 +1464,12 @@ int pycnn_b200_train_epoch(pycnn_b200_ctx* c, const int64_t* perm, int64_t n, in
     const int64_t len = end - start, per = ceil_div(len, W);
     return (int)(std::min(len, per * (R + 1)) - std::min(len, per * R));
   };
-  const bool pipelined = c->use_prefetch && num_batches > 1;
+  // gather-free when every batch of this rank is large enough for the 2-SM layer-1 GEMMs (they fetch their rows from the
+  // dataset themselves); otherwise the gathered batch buffer, double-buffered behind the previous step when it pays
+  bool gf = true;
+  for (int64_t start = 0; start < n && gf; start += batch_size)
+    if (local_bs(start) > 0) gf = gather_free_ok(c, local_bs(start));
+  const bool pipelined = !gf && c->use_prefetch && num_batches > 1;
   if (pipelined) {
     PB_TRY(ensure_prefetch_buffers(c));
     PB_TRY(prime_rows(c, local_bs(0)));
@@ -1412,7 +1480,7 @@ int pycnn_b200_train_epoch(pycnn_b200_ctx* c, const int64_t* perm, int64_t n, in
     // one graph per distinct local batch size (x next size x buffer parity when the row gather is pipelined);
     // runs of full batches go graph_steps at a time
     int count = 1;
-    if (pipelined && parity == 0 && bs > 0) {
+    if ((pipelined || gf) && parity == 0 && bs > 0) {
       // largest power-of-two run (<= graph_steps) of full batches that starts here: an epoch decomposes greedily
       // into 16, 8, 4, 2, 1-step graphs, so only a handful of graphs are ever instantiated
       for (int U = 1; 2 * U <= c->graph_steps; ) {
@@ -1423,11 +1491,12 @@ int pycnn_b200_train_epoch(pycnn_b200_ctx* c, const int64_t* perm, int64_t n, in
         count = U;
       }
     }
-    if (pipelined) PB_TRY(graphed_step_rows_pf(c, bs, local_bs(start + count * (int64_t)batch_size), parity, count));
-    else           PB_TRY(graphed_step_rows(c, bs, 0, bs));
+    if (gf && bs > 0)   PB_TRY(graphed_step_rows_gf(c, bs, count));
+    else if (pipelined) PB_TRY(graphed_step_rows_pf(c, bs, local_bs(start + count * (int64_t)batch_size), parity, count));
+    else                PB_TRY(graphed_step_rows(c, bs, 0, bs));
     if (c->update_rule == PYCNN_B200_RULE_CUPY && c->opt == PYCNN_B200_OPT_ADAM) c->t += count;
     start += count * (int64_t)batch_size;
-    if (count & 1) parity ^= 1;
+    if (!gf && (count & 1)) parity ^= 1;
   }
   PB_TRY(read_stats(c, loss_sum, correct, true));
   return 0;

@@ -139,12 +139,21 @@ struct pycnn_b200_ctx {
   int last_gemm_ctas = 0;              // grid size of the most recent tensor-core GEMM launch
   bool defer_last_dw = true;           // backward: dW of layer 2 runs on the SMs dW of layer 1 leaves idle (PYCNN_B200_DEFER_DW=0)
   bool use_prefetch = true;
+  bool pf_early = false;               // fork the next step's row gather BEFORE the layer-1 forward GEMM instead of behind it (PYCNN_B200_PF_EARLY=1)
   int graph_steps = 16;                // max training steps per captured graph: a graph launch costs ~15 us of idle GPU (PYCNN_B200_GRAPH_STEPS)
   int pf_ctas_per_sm = 2;              // gather CTAs per SM on the prefetch stream (PYCNN_B200_PF_CTAS)
   bool uniform_carveout = true;        // elementwise kernels ask for the GEMMs' L1/shared split (PYCNN_B200_CARVEOUT=0 disables)
   bool fuse_softmax = true;            // training: softmax/CE/dZ in the output-layer GEMM's epilogue (PYCNN_B200_FUSE_SOFTMAX=0: own kernel)
   bool one_wave_tiles = true;          // shallow-K GEMMs: widen the tile rather than run a second wave (PYCNN_B200_ONE_WAVE=0 disables)
   bool nvtx = false;                   // NVTX range per kernel class around every launch / capture (PYCNN_B200_NVTX=1)
+  // layer-1 GEMMs fetch their batch rows from the dataset by TMA tile::gather4 -- no gathered batch in HBM (PYCNN_B200_GATHER_FREE=1).
+  // Correct (bit-identical) but OFF by default: measured on B200, a gather4 op (4 rows x 128 B) costs ~70 SM cycles of the TMA
+  // unit, 32 ops per 16 KB operand tile = 2240 cycles against the tile's 760 MMA cycles: layer-1 forward 22 -> 50 us, dW 22 -> 62 us.
+  bool use_gather_free = false;
+  struct GatherSrc {                   // set around a step whose batch is "rows idx[cursor + ...] of the dataset" (no d_x)
+    bool on = false;
+    int64_t advance = 0;               // rows the step's bookkeeping moves the cursor on by (dW of layer 1 looks back by it)
+  } gsrc;
   bool use_tail = true;                // forward layers 2.. + softmax + the dA chain as one kernel (tail_fused.cuh; PYCNN_B200_FUSED_TAIL=0 disables)
   bool use_two_sm = true;              // deep 256-wide GEMM tiles run as CTA pairs on the 2-SM tensor-core path (PYCNN_B200_TWO_SM=0 disables)
   int pair_min_kb = 64;                // pairing pays from this many k-blocks per CTA on (PYCNN_B200_PAIR_MIN_KB)

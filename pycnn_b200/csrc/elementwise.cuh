@@ -184,6 +184,16 @@ __device__ __forceinline__ void stats_add(unsigned long long* stats, double loss
   if (correct) atomicAdd(&stats[1], correct);
 }
 
+// gather-free steps: only the labels of the batch are gathered (bs x 4 bytes); the feature rows are fetched by the layer-1
+// GEMMs themselves
+__global__ void gather_labels_kernel(const int32_t* __restrict__ labels, const int64_t* __restrict__ idx_base,
+                                     const int64_t* __restrict__ cursor, int bs, int32_t* __restrict__ blabels) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int64_t* idx = idx_base + (cursor ? cursor[0] : 0);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < bs; i += gridDim.x * blockDim.x) blabels[i] = labels[idx[i]];
+}
+
 __global__ void advance_cursor_kernel(int64_t* cursor, int64_t advance) {   // tail of the prefetch branch
   if (threadIdx.x == 0) cursor[0] += advance;
 }
@@ -283,6 +293,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
                                                      float* __restrict__ part, int64_t ld_part, int rows_per_block) {
   __shared__ double red[8][33];
   pdl_wait();
+  pdl_launch_dependents();
   const int n = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(bs, r0 + rows_per_block);

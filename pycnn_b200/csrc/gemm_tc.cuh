@@ -43,7 +43,8 @@ struct GemmCfg {
   // refused on this part ("cluster misconfiguration", seen at 225 KB), and 6 x 32 KB stages are deep enough
   static constexpr int MAX_STAGES = (208 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int GATHER_IDX = 2048;                // row indices a CTA of the gather-free form stages (TWO only)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + (TWO ? GATHER_IDX * 4 : 0);
 };
 
 struct TcGemmArgs {
@@ -75,6 +76,12 @@ struct TcGemmArgs {
   float* db_part;      // db_o partial of this row tile: db_part[blockIdx.y * lddz + j]
   StepBookkeeping bk;
   unsigned long long* trace;   // timeline slot (diagnostics) or nullptr
+  // Gather-free layer-1 GEMMs (2-SM kernels only): the batch rows are rows idx[*cursor + extra + i] of the DATASET, fetched by
+  // TMA tile::gather4 straight into the operand stage -- forward: A rows (map_a = dataset, box {32, 1}); dW: B k-rows
+  // (map_b = dataset, box {32, 1}, 32-byte-atom swizzle).  No gathered copy of the batch ever exists in HBM.
+  const int64_t* gather_idx;
+  const int64_t* gather_cursor;
+  int64_t gather_extra;
 };
 
 // ---- thread-block cluster helpers (split-K reduction through distributed shared memory) ----
@@ -248,7 +255,57 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   trace_begin(g.trace);
 
   if (warp == 0) {
-    if (lane == 0) {
+    bool gathered = false;
+    if constexpr (TWO && A_MN == B_MN) {
+      if (g.gather_idx) {
+        // ===== TMA producer, gather-free form: the whole warp issues, one tile::gather4 (4 dataset rows x 32 floats) per
+        // lane and k-block.  Forward: lane l owns batch rows m0 + 4l .. +3 of the A tile for the whole loop; dW: the B
+        // tile of k-block i is batch rows 32 i .. +31, lane l = (N atom l / 8, row quad l % 8), indices staged in smem.
+        gathered = true;
+        const int64_t* idx = g.gather_idx + (g.gather_cursor ? g.gather_cursor[0] : 0) + g.gather_extra;
+        int32_t* s_idx = reinterpret_cast<int32_t*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+        int r4[4] = {-1, -1, -1, -1};
+        if constexpr (!A_MN) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int row = m0 + 4 * lane + j;
+            if (row < g.M) r4[j] = (int)idx[row];
+          }
+        } else {
+          for (int i = lane; i < nkb * 32; i += 32) {
+            const int row = kb0 * 32 + i;
+            s_idx[i] = row < g.K ? (int)idx[row] : -1;
+          }
+          __syncwarp();
+        }
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (i / STAGES) & 1;
+          if (lane == 0) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            if (pair_half == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+          }
+          __syncwarp();
+          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          const int k0 = (kb0 + i) * G_BK;
+          const uint32_t lead_full = map_to_cta(smem_u32(&full_bar[s]), cluster_ctarank() & ~1u);
+          if constexpr (!A_MN) {
+            tma_gather4_2sm(sa + lane * 512, &map_a, lead_full, k0, r4[0], r4[1], r4[2], r4[3]);
+            if (lane == 0) tma_load_2d_2sm(sb, &map_b, lead_full, k0, n0 + (int)pair_half * (BN / 2));
+          } else {
+            if (lane < G_BM / 32) tma_load_2d_2sm(sa + lane * (G_BK * 128), &map_a, lead_full, m0 + lane * 32, k0);
+            const int a2 = lane >> 3, gq = lane & 7;
+            if (a2 < BN / 64) {
+              const int32_t* ri = s_idx + i * 32 + gq * 4;
+              tma_gather4_2sm(sb + a2 * (G_BK * 128) + gq * 512, &map_b, lead_full,
+                              n0 + ((int)pair_half * (BN / 64) + a2) * 32, ri[0], ri[1], ri[2], ri[3]);
+            }
+          }
+        }
+      }
+    }
+    if (!gathered && lane == 0) {
       // ===== TMA producer =====
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
@@ -624,6 +681,24 @@ static inline int make_map_mnmajor(pycnn_b200_ctx* c, CUtensorMap* map, const fl
   return 0;
 }
 
+// Row-gather maps (tile::gather4): the dataset [rows, width] row-major with a box of ONE row x 32 floats; K-major operand
+// tiles use the plain 128-byte swizzle, MN-major ones the 32-byte-atom form (same smem layouts as the tiled boxes).
+static inline int make_map_gather(pycnn_b200_ctx* c, CUtensorMap* map, const float* base, int64_t rows, int64_t width, int64_t ld,
+                                  bool mn_major) {
+  PB_TRY(resolve_encode_tiled(c));
+  PB_CHECK((ld & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand needs 16-byte aligned rows (ld=%lld)", (long long)ld);
+  cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 1};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(c->encode_tiled)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(row gather rows=%lld width=%lld) failed: %d", (long long)rows, (long long)width, (int)r);
+  return 0;
+}
+
 struct GemmCall {
   const float* A; int64_t lda; bool a_kmajor;  // kmajor: [M,K] row-major; else [K,M] row-major
   const float* B; int64_t ldb; bool b_kmajor;  // kmajor: [N,K] row-major; else [K,N] row-major
@@ -639,6 +714,9 @@ struct GemmCall {
   // epi == 4: fused softmax / cross-entropy / dZ epilogue of the output layer (C is not written); db_slot = bias tensor
   const int32_t* labels; float* dz; int64_t lddz; unsigned long long* stats; int db_slot; StepBookkeeping bk;
   int max_ctas;       // > 0: cap tiles x split (a GEMM meant to run on the SMs another kernel leaves idle)
+  // gather-free form (layer-1 forward: A; layer-1 dW: B): the operand is the DATASET [gather_rows, K|N] and its batch rows
+  // are rows gather_idx[*gather_cursor + gather_extra + i]; only honoured on the 2-SM path (gather_ok tells the caller)
+  const int64_t* gather_idx; const int64_t* gather_cursor; int64_t gather_extra; int64_t gather_rows;
 };
 
 // how many clusters of S CTAs (S = 2, 4, 8 -> slot 0, 1, 2) of each instantiation the device can hold at once;
@@ -816,6 +894,13 @@ static GemmPlan plan_tc_gemm(const pycnn_b200_ctx* c, const GemmCall& g) {
   return p;
 }
 
+// can this call run gather-free (2-SM path, indices of a k-slice fit the kernel's staging)?
+static bool gather_ok(const pycnn_b200_ctx* c, const GemmCall& g) {
+  const GemmPlan p = plan_tc_gemm(c, g);
+  const bool dw = !g.a_kmajor && !g.b_kmajor;
+  return p.two && (g.a_kmajor == g.b_kmajor) && (!dw || p.kb_per_split * 32 <= tc::GemmCfg<256, true>::GATHER_IDX);
+}
+
 static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   PB_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "tc_gemm: empty problem");
   PB_CHECK(!( !g.a_kmajor && g.b_kmajor), "tc_gemm: (A MN-major, B K-major) is not instantiated");
@@ -825,10 +910,15 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   const int BN = p.BN, split = p.split;
   const bool partial = split > 1 && !p.cluster;
   CUtensorMap ma, mb;
-  if (g.a_kmajor) PB_TRY(make_map_kmajor(c, &ma, g.A, g.M, g.K, g.lda, tc::G_BM));
-  else            PB_TRY(make_map_mnmajor(c, &ma, g.A, g.K, g.M, g.lda));
-  if (g.b_kmajor) PB_TRY(make_map_kmajor(c, &mb, g.B, g.N, g.K, g.ldb, (p.pair || p.two) ? BN / 2 : BN));
-  else            PB_TRY(make_map_mnmajor(c, &mb, g.B, g.K, g.N, g.ldb));
+  const bool gather_a = g.gather_idx && g.a_kmajor && g.b_kmajor, gather_b = g.gather_idx && !g.a_kmajor && !g.b_kmajor;
+  PB_CHECK(!g.gather_idx || (p.two && (gather_a || gather_b) && (gather_a || p.kb_per_split * 32 <= tc::GemmCfg<256, true>::GATHER_IDX)),
+           "tc_gemm: the gather-free form needs the 2-SM path (ask gather_ok first)");
+  if (gather_a)        PB_TRY(make_map_gather(c, &ma, g.A, g.gather_rows, g.K, g.lda, false));
+  else if (g.a_kmajor) PB_TRY(make_map_kmajor(c, &ma, g.A, g.M, g.K, g.lda, tc::G_BM));
+  else                 PB_TRY(make_map_mnmajor(c, &ma, g.A, g.K, g.M, g.lda));
+  if (gather_b)        PB_TRY(make_map_gather(c, &mb, g.B, g.gather_rows, g.N, g.ldb, true));
+  else if (g.b_kmajor) PB_TRY(make_map_kmajor(c, &mb, g.B, g.N, g.K, g.ldb, (p.pair || p.two) ? BN / 2 : BN));
+  else                 PB_TRY(make_map_mnmajor(c, &mb, g.B, g.K, g.N, g.ldb));
   dim3 grid(p.tiles_n, (p.pair || p.two) ? (unsigned)round_up(p.tiles_m, 2) : p.tiles_m, split);
   tc::TcGemmArgs a{};
   a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.N = g.N; a.K = g.K;
@@ -838,6 +928,7 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
   a.cluster_reduce = p.cluster ? 1 : 0;
   a.pair = (p.pair || p.two) ? 1 : 0;
   a.labels = g.labels; a.dz = g.dz; a.lddz = g.lddz; a.stats = g.stats; a.bk = g.bk;
+  a.gather_idx = g.gather_idx; a.gather_cursor = g.gather_cursor; a.gather_extra = g.gather_extra;
   const int64_t tile_floats = (int64_t)(g.M - 1) * g.ldc + round_up(g.N, 4);
   if (g.grad_slot) {                      // gradient tensor: ordered partials in its arena region (or C itself when unsplit)
     GradPartSlot& gs = c->gp[g.grad_slot - 1];

@@ -97,11 +97,27 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const void* map, uint
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// tile::gather4, CTA-pair form: FOUR rows of a 2-D tensor, picked by index, land as 4 consecutive 128-byte rows at dst
+// (the smem swizzle is a function of the address, as for tiled boxes); rows outside the tensor read as zeros
+__device__ __forceinline__ void tma_gather4_2sm(void* dst, const void* map, uint32_t bar_cluster_addr, int c0, int r0, int r1,
+                                                int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const void* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// TMA store: a [box] tile in smem (same swizzled layout a load of that box would produce) -> global, bulk-group completion;
+// rows / columns of the box that fall outside the tensor are clipped
+__device__ __forceinline__ void tma_store_2d(const void* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
 }
 // 1-D bulk copies (no tensor map): global -> smem with mbarrier completion, smem -> global with bulk groups
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {

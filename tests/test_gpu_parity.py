@@ -624,7 +624,7 @@ def _epoch_run(lib, env, monkeypatch, mode, opt, n=2100, bs=128, epochs=2, S=32,
     (loss, correct) and the final parameters."""
     for k in ("PYCNN_B200_PREFETCH", "PYCNN_B200_GRAPH_STEPS", "PYCNN_B200_FUSE_SOFTMAX", "PYCNN_B200_CLUSTER_SPLITK",
               "PYCNN_B200_FORK", "PYCNN_B200_PDL", "PYCNN_B200_GRAPHS", "PYCNN_B200_CARVEOUT", "PYCNN_B200_DEFER_DW",
-              "PYCNN_B200_FUSED_TAIL", "PYCNN_B200_TWO_SM"):
+              "PYCNN_B200_FUSED_TAIL", "PYCNN_B200_TWO_SM", "PYCNN_B200_GATHER_FREE"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -680,6 +680,18 @@ def test_prefetch_pipeline_visits_every_row_once(lib, monkeypatch, S, bs, layers
         assert got[0] == want[0]
         for a, bb in zip(want[1], got[1]):
             np.testing.assert_array_equal(bb, a)
+
+
+def test_gather_free_layer1_gemms_equal_the_gathered_batch(lib, monkeypatch):
+    """Opt-in gather-free form (PYCNN_B200_GATHER_FREE=1; off by default: the TMA unit's gather4 rate makes it slower,
+    DESIGN.md): the batch is never materialised, forward and dW of layer 1 fetch rows idx[...] of the dataset by TMA gather4 (forward_pass.pyx:29 / backward_pass.pyx:92 on pycnn.py:629's batch_x).  Same
+    rows, same tile layout, same k order: bit-identical to the path that gathers the batch with a copy kernel first."""
+    kw = dict(n=3 * 4096 + 1000, bs=4096, epochs=2, layers=(256, 128, 64))
+    a = _epoch_run(lib, {"PYCNN_B200_GATHER_FREE": "1"}, monkeypatch, "tf32", "adam", **kw)
+    b = _epoch_run(lib, {"PYCNN_B200_GATHER_FREE": "0"}, monkeypatch, "tf32", "adam", **kw)
+    assert a[0] == b[0]
+    for x, y in zip(a[1], b[1]):
+        np.testing.assert_array_equal(x, y)
 
 
 @pytest.mark.parametrize("mode,opt", [("tf32", "adam"), ("tf32", "sgd"), ("fp32", "adam")])
