@@ -1853,7 +1853,9 @@ int pycnn_b200_comm_destroy(pycnn_b200_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     drop_graphs(c);
     NcclApi* api = nccl_api();
-    if (api) api->CommDestroy(c->nccl_comm);
+    // the stream is drained; ncclCommAbort releases the communicator without waiting for the peers (ncclCommDestroy can
+    // block for ever when a peer has already died -- e.g. while an exception unwinds on one rank)
+    if (api) { if (api->CommAbort) api->CommAbort(c->nccl_comm); else api->CommDestroy(c->nccl_comm); }
     c->nccl_comm = nullptr;
   }
   c->rank = 0;

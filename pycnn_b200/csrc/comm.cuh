@@ -23,6 +23,7 @@ struct NcclApi {
   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*CommDestroy)(NcclComm) = nullptr;
   int (*CommGetAsyncError)(NcclComm, int*) = nullptr;
+  int (*CommAbort)(NcclComm) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   int (*GetVersion)(int*) = nullptr;
 };
@@ -52,6 +53,7 @@ static inline NcclApi* nccl_api() {
   api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t)>(
       dlsym(h, "ncclAllReduce"));
   api.CommDestroy = reinterpret_cast<int (*)(NcclComm)>(dlsym(h, "ncclCommDestroy"));
+  api.CommAbort = reinterpret_cast<int (*)(NcclComm)>(dlsym(h, "ncclCommAbort"));
   api.CommGetAsyncError = reinterpret_cast<int (*)(NcclComm, int*)>(dlsym(h, "ncclCommGetAsyncError"));
   api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
   api.GetVersion = reinterpret_cast<int (*)(int*)>(dlsym(h, "ncclGetVersion"));
