@@ -44,8 +44,8 @@ def launches():
         f.write("id,kernel,grid,block,time_us\n")
         for i, (n, (_, t, g, b)) in enumerate(zip(names, rows)):
             f.write(f"{i},{n},\"{g}\",\"{b}\",{t / 1000:.3f}\n")
-    # one steady-state resident step: between two consecutive gather_rows launches
-    idx = [i for i, n in enumerate(names) if "gather_rows" in n]
+    # one steady-state resident step: between two consecutive layer-1 forward GEMM launches
+    idx = [i for i, n in enumerate(names) if "gemm_tf32_kernel<256, 0, 0, 1>" in n]
     if len(idx) >= 6:
         s, e = idx[4], idx[5]
         tot = sum(rows[i][1] for i in range(s, e))
@@ -89,6 +89,16 @@ report("prof_extract.ncu-rep", "extract")
 report("prof_elem.ncu-rep", "elementwise")
 if TRAFFIC:
     import json
+    # bench.py's kernel classes -> the captured launch that class consists of (BASELINE configs[1] shapes)
+    classes = {"gemm_forward_layer1": ("gemm_tf32_kernel<256, 0, 0, 1>", "(32, 1, 4)"), "gemm_dW_layer1": ("gemm_tf32_kernel<256, 1, 1, 1>", "(2, 17, 4)"),
+               "gemm_forward_tail": ("tail_fused_kernel", "(32, 1, 1)"), "gather_rows": ("gather_rows_kernel", "(296, 1, 1)"),
+               "clip_update": ("clip_update_kernel", ""), "grad_finalize": ("grad_finalize_kernel", ""),
+               "extract_conv_relu_pool": ("extract_tc_kernel", "")}
+    by_class = {}
+    for cls, (kern, grid) in classes.items():
+        hits = [v for k, v in TRAFFIC.items() if kern in k and (not grid or k.endswith(grid))]
+        if hits:
+            by_class[cls] = hits[-1]
     with open(os.path.join(out_dir, f"{tag}_traffic.json"), "w") as f:
         json.dump({"source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures of bench.py (cold L2)",
-                   "bytes_per_launch": TRAFFIC}, f, indent=1, sort_keys=True)
+                   "bytes_per_launch": TRAFFIC, "c1": by_class}, f, indent=1, sort_keys=True)
