@@ -210,6 +210,10 @@ int extract_device(pycnn_b200_ctx* c, const uint8_t* d_images, int64_t n, int S,
 // ---------------------------------------------------------------------------------------------
 
 int issue_prefetch(pycnn_b200_ctx* c);
+// Where the next step's row gather (HBM-bound, ~30-39 us) is forked.  Single GPU: behind the layer-1 forward GEMM, beside the
+// latency-bound tail.  Data parallel: behind the layer-1 dW GEMM, beside the gradient exchange -- that phase is NVLink-
+// latency-bound with HBM idle, as long as the gather itself, and the tail / dW GEMMs then run undisturbed.
+bool pf_behind_dw1(const pycnn_b200_ctx* c) { return c->pf_place == 2 || (c->pf_place == 0 && c->world > 1); }
 
 // Gradients are never accumulated with atomics and the flat gradient buffer is never zero-filled: every producer
 // either writes a tensor's gradient whole or stores ordered partial sums (GradPartSlot) that finalize_grads adds in
@@ -273,7 +277,7 @@ int forward_logits(pycnn_b200_ctx* c, const float* x, int bs, const int32_t* tra
     }
     if (l == 0 && c->pf_early) PB_TRY(issue_prefetch(c));   // no-op unless a pipelined training step armed it
     PB_TRY(gemm(c, g));
-    if (l == 0) PB_TRY(issue_prefetch(c));
+    if (l == 0 && !pf_behind_dw1(c)) PB_TRY(issue_prefetch(c));
     in = g.C;
   }
   return 0;
@@ -378,6 +382,7 @@ int backward_dw_after_tail(pycnn_b200_ctx* c, const float* x, int bs) {
   if (fork) PB_CUDA(cudaEventRecord(c->ev_fork[0], main_stream));
   PB_TRY(gemm(c, dw_call(0)));
   const int room = c->num_sms - c->last_gemm_ctas;
+  if (pf_behind_dw1(c)) PB_TRY(issue_prefetch(c));
   if (fork) {
     PB_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork[0], 0));
     c->stream = c->side_stream;
@@ -450,6 +455,7 @@ int backward(pycnn_b200_ctx* c, const float* x, int bs) {
       if (have_deferred && l == 1) PB_CUDA(cudaEventRecord(c->ev_fork[1], main_stream));   // = dW_1's dependency
     }
   }
+  if (pf_behind_dw1(c)) PB_TRY(issue_prefetch(c));
   if (have_deferred) {
     const int room = c->num_sms - c->last_gemm_ctas;      // last launch on this path: dW of layer 1
     if (room >= 8) deferred.max_ctas = room;
@@ -941,6 +947,7 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_PF_CTAS"); if (g && atoi(g) > 0) c->pf_ctas_per_sm = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PREFETCH"); if (g && g[0] == '0') c->use_prefetch = false; }
   { const char* g = getenv("PYCNN_B200_PF_EARLY"); if (g) c->pf_early = (g[0] == '1'); }
+  { const char* g = getenv("PYCNN_B200_PF_PLACE"); if (g) c->pf_place = !strcmp(g, "fwd") ? 1 : !strcmp(g, "dw") ? 2 : 0; }
   { const char* g = getenv("PYCNN_B200_FUSE_SOFTMAX"); if (g && g[0] == '0') c->fuse_softmax = false; }
   { const char* g = getenv("PYCNN_B200_ONE_WAVE"); if (g && g[0] == '0') c->one_wave_tiles = false; }
   { const char* g = getenv("PYCNN_B200_PAIR"); if (g && g[0] == '0') c->use_pair = false; }

@@ -139,6 +139,7 @@ struct pycnn_b200_ctx {
   int last_gemm_ctas = 0;              // grid size of the most recent tensor-core GEMM launch
   bool defer_last_dw = true;           // backward: dW of layer 2 runs on the SMs dW of layer 1 leaves idle (PYCNN_B200_DEFER_DW=0)
   bool use_prefetch = true;
+  int pf_place = 0;                    // row-gather fork point: 0 auto (1 GPU: behind layer-1 forward; DP: behind layer-1 dW), 1 fwd, 2 dw (PYCNN_B200_PF_PLACE)
   bool pf_early = false;               // fork the next step's row gather BEFORE the layer-1 forward GEMM instead of behind it (PYCNN_B200_PF_EARLY=1)
   int graph_steps = 16;                // max training steps per captured graph: a graph launch costs ~15 us of idle GPU (PYCNN_B200_GRAPH_STEPS)
   int pf_ctas_per_sm = 2;              // gather CTAs per SM on the prefetch stream (PYCNN_B200_PF_CTAS)

@@ -453,7 +453,13 @@ struct UpdateParams {
 // block of a tensor (and every run) arrives at the same bits
 __device__ __forceinline__ double tensor_norm2(const double* __restrict__ chunk_norm, const Chunk& ch, double* s8) {
   double a = 0.0;
-  for (int i = threadIdx.x; i < ch.n_chunks; i += blockDim.x) a += __ldcg(chunk_norm + ch.first_chunk + i);
+  for (int i0 = threadIdx.x; i0 < ch.n_chunks; i0 += 4 * blockDim.x) {      // independent L2 loads, added in chunk order
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (i0 + u * (int)blockDim.x < ch.n_chunks) ? __ldcg(chunk_norm + ch.first_chunk + i0 + u * blockDim.x) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a += v[u];
+  }
   return block_sum_d(a, s8);
 }
 

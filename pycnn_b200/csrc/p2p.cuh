@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chun
   }
   if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->grads_ready[threadIdx.x], seq, t.lost, threadIdx.x);
   __syncthreads();
+  if (threadIdx.x == 0) trace_mark(trace, 1);          // every rank's gradient is ready
   __shared__ double sh[8];
   if ((int)blockIdx.x < t.nchunks) {
     const Chunk ch = chunks[t.chunk0 + blockIdx.x];
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chun
       chunk_norm[t.chunk0 + blockIdx.x] = tot;
     }
   }
+  if (threadIdx.x == 0) trace_mark(trace, 2);          // owned chunks reduced
   // the last block to finish publishes this rank's per-tensor partial norms to every rank.  One fence per block,
   // after the block barrier: fences are cumulative, so it also orders the other threads' stores (a fence in every
   // thread costs a MEMBAR per warp and showed up as microseconds).
@@ -160,7 +162,13 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chun
       const int2 tc = tensor_chunks[k];
       const int lo = max(tc.x, t.chunk0), hi = min(tc.x + tc.y, t.chunk0 + t.nchunks);
       double a = 0.0;
-      for (int i = lo + lane; i < hi; i += 32) a += __ldcg(&chunk_norm[i]);
+      for (int i0 = lo + lane; i0 < hi; i0 += 32 * 8) {      // 8 independent L2 loads in flight per lane, added in chunk order
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (i0 + 32 * u < hi) ? __ldcg(&chunk_norm[i0 + 32 * u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a += v[u];
+      }
       a = warp_sum_d(a);
       if (lane < t.world) t.sync[lane]->norms[t.rank][k] = a;
     }
@@ -190,6 +198,7 @@ __global__ void __launch_bounds__(256) p2p_update_kernel(PeerTable t, const Chun
     if (u.rule == 0) {   // norms of the fully reduced gradient: every rank's partials, summed in rank order
       if (threadIdx.x < t.world) wait_flag(&t.sync[t.rank]->norms_ready[threadIdx.x], seq, t.lost, threadIdx.x);
       __syncthreads();
+      if (threadIdx.x == 0) trace_mark(trace, 1);      // every rank's partial norms are here
       if (threadIdx.x == 0) {
         double n2 = 0.0;
         for (int r = 0; r < t.world; ++r) n2 += __ldcv(&t.sync[t.rank]->norms[r][ch.tensor]);
@@ -224,6 +233,7 @@ __global__ void __launch_bounds__(256) p2p_update_kernel(PeerTable t, const Chun
       }
     }
   }
+  if (threadIdx.x == 0) trace_mark(trace, 2);          // owned chunks updated, parameter stores issued to every rank
   // completion: the last block of this rank publishes "my parameter writes are done" and waits for all peers
   // (one cumulative system-scope fence per block, behind the block barrier, instead of one per thread)
   __syncthreads();

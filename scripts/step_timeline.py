@@ -70,6 +70,6 @@ if len(starts_t) >= 1:
     for name, sid, a, b, *marks in ev_sorted:
         if t0 <= a < t1:
             ph = "  ".join(f"{lbl} {(m[0] - a) / 1e3:.1f}..{(m[1] - a) / 1e3:.1f}" for lbl, m in
-                           zip(("first-stage", "accum-done", "parked"), marks) if m)
+                           zip(("first-stage", "accum-done", "parked") if name.startswith("gemm") else ("m1", "m2", "m3"), marks) if m)
             print(f"{name:24s} {sid:6d} {(a - t0) / 1e3:9.2f} {(b - t0) / 1e3:9.2f} {(b - a) / 1e3:8.2f}   {ph}")
 ctx.close()
