@@ -503,6 +503,12 @@ int apply_update(pycnn_b200_ctx* c, bool norms_ready = false) {
     PB_CUDA(launch_pdl(c, grad_sqnorm_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, (const float*)c->d_grads,
                        (const Chunk*)c->d_chunks, c->d_chunk_norm, trace_slot(c, KC_SQNORM)));
   }
+  if (c->update_rule == PYCNN_B200_RULE_CPU && c->big_tensors) {     // per-tensor totals once, not once per block
+    LaunchScope ls(c, KC_SQNORM);
+    PB_CUDA(launch_pdl(c, tensor_norm_kernel, dim3((unsigned)c->tensors.size()), dim3(256), 0, c->stream, (const double*)c->d_chunk_norm,
+                       (const int2*)c->d_tensor_chunks, c->d_tensor_norm));
+    u.tensor_norm = c->d_tensor_norm;
+  }
   LaunchScope ls(c, KC_UPDATE);
   PB_CUDA(launch_pdl(c, clip_update_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, c->d_params,
                      (const float*)c->d_grads, c->d_m, c->d_v, (const Chunk*)c->d_chunks, (const double*)c->d_chunk_norm, u,
@@ -857,6 +863,7 @@ void free_network(pycnn_b200_ctx* c) {
   free_workspace(c);
   free_dev(c->d_params); free_dev(c->d_grads); free_dev(c->d_m); free_dev(c->d_v);
   free_dev(c->d_chunks); free_dev(c->d_chunk_norm); free_dev(c->d_tensor_chunks); c->d_tensor_chunks = nullptr;
+  free_dev(c->d_tensor_norm); c->d_tensor_norm = nullptr;
   c->d_params = c->d_grads = c->d_m = c->d_v = nullptr;
   c->d_chunks = nullptr; c->d_chunk_norm = nullptr;
   c->tensors.clear(); c->dims.clear(); c->ldw.clear();
@@ -1231,6 +1238,9 @@ int pycnn_b200_set_network(pycnn_b200_ctx* c, int64_t D, const int* layers, int 
   PB_CUDA(cudaMalloc(&c->d_tensor_chunks, sizeof(int2) * tchunks.size()));
   PB_CUDA(cudaMemcpy(c->d_tensor_chunks, tchunks.data(), sizeof(int2) * tchunks.size(), cudaMemcpyHostToDevice));
   c->h_chunks = chunks;
+  c->big_tensors = false;
+  for (const int2& tcn : tchunks) c->big_tensors = c->big_tensors || tcn.y > 2048;
+  PB_CUDA(cudaMalloc(&c->d_tensor_norm, sizeof(double) * tchunks.size()));
   PB_CUDA(cudaMalloc(&c->d_chunk_norm, sizeof(double) * chunks.size()));
   PB_CUDA(cudaMemset(c->d_chunk_norm, 0, sizeof(double) * chunks.size()));
   c->t = 0;

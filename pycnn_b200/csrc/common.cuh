@@ -186,6 +186,8 @@ struct pycnn_b200_ctx {
   int num_chunks = 0;
   std::vector<pb::Chunk> h_chunks;      // host copy of the chunk table
   int2* d_tensor_chunks = nullptr;      // per tensor: (first chunk, chunk count)
+  double* d_tensor_norm = nullptr;      // [tensors] ||g||^2 per tensor (large networks only: tensor_norm_kernel)
+  bool big_tensors = false;             // some tensor has more chunks than an update block should add up by itself
   double* d_chunk_norm = nullptr;       // [num_chunks] sum of squares of each chunk of the (reduced) gradient
   float* d_gpart = nullptr;             // ordered-partial-sum arena (sized by ensure_workspace for the batch capacity)
   int64_t gpart_floats = 0;

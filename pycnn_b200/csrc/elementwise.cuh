@@ -442,6 +442,8 @@ __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restric
 }
 
 struct UpdateParams {
+  const double* tensor_norm;   // per-tensor ||g||^2 formed by tensor_norm_kernel, or nullptr: every block adds its tensor's chunk
+                               // values itself (cheaper than a launch for small networks, quadratic for large ones)
   int opt;       // 0 sgd, 1 adam
   int rule;      // 0 cpu (clip + skip), 1 cupy
   float lr, beta1, beta2, eps, inv_bc1, inv_bc2, eps2, max_norm;
@@ -461,6 +463,25 @@ __device__ __forceinline__ double tensor_norm2(const double* __restrict__ chunk_
     for (int u = 0; u < 4; ++u) a += v[u];
   }
   return block_sum_d(a, s8);
+}
+
+// large networks: one block per tensor adds the tensor's chunk values in chunk order (fixed-shape reduction)
+__global__ void __launch_bounds__(256) tensor_norm_kernel(const double* __restrict__ chunk_norm, const int2* __restrict__ tensor_chunks,
+                                                          double* __restrict__ tensor_norm) {
+  __shared__ double s8[8];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int2 tc = tensor_chunks[blockIdx.x];
+  double a = 0.0;
+  for (int i0 = threadIdx.x; i0 < tc.y; i0 += 8 * blockDim.x) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (i0 + u * (int)blockDim.x < tc.y) ? __ldcg(chunk_norm + tc.x + i0 + u * blockDim.x) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a += v[u];
+  }
+  const double t = block_sum_d(a, s8);
+  if (threadIdx.x == 0) tensor_norm[blockIdx.x] = t;
 }
 
 __device__ __forceinline__ void adam_or_sgd4(float4& p, float4& mm, float4& vv, const float4& g, float scale,
@@ -524,7 +545,7 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ pa
     }
   }
   if (u.rule == 0) {
-    const double n2 = tensor_norm2(chunk_norm, ch, s8);
+    const double n2 = u.tensor_norm ? __ldcg(u.tensor_norm + ch.tensor) : tensor_norm2(chunk_norm, ch, s8);
     if (!isfinite(n2)) return;  // NaN/Inf gradient: skip this tensor's update
     const double nrm = sqrt(n2);
     if (nrm > (double)u.max_norm) scale = (float)((double)u.max_norm / nrm);

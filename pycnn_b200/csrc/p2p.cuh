@@ -155,22 +155,21 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(PeerTable t, const Chun
   }
   __syncthreads();
   if (last) {
-    // per tensor: the owned chunks' sums of squares, added in chunk order by one warp (lanes stride the range, then a
-    // fixed shuffle tree) -- the same bits every run -- and stored into every rank's sync block
-    const int lane = threadIdx.x & 31;
-    for (int k = threadIdx.x >> 5; k < ntensors; k += (int)(blockDim.x >> 5)) {
+    // per tensor: the owned chunks' sums of squares, added in chunk order by the whole block (independent loads, then a
+    // fixed-shape reduction) -- the same bits every run -- and stored into every rank's sync block
+    for (int k = 0; k < ntensors; ++k) {
       const int2 tc = tensor_chunks[k];
       const int lo = max(tc.x, t.chunk0), hi = min(tc.x + tc.y, t.chunk0 + t.nchunks);
       double a = 0.0;
-      for (int i0 = lo + lane; i0 < hi; i0 += 32 * 8) {      // 8 independent L2 loads in flight per lane, added in chunk order
+      for (int i0 = lo + (int)threadIdx.x; i0 < hi; i0 += 8 * (int)blockDim.x) {
         double v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = (i0 + 32 * u < hi) ? __ldcg(&chunk_norm[i0 + 32 * u]) : 0.0;
+        for (int u = 0; u < 8; ++u) v[u] = (i0 + u * (int)blockDim.x < hi) ? __ldcg(&chunk_norm[i0 + u * blockDim.x]) : 0.0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) a += v[u];
       }
-      a = warp_sum_d(a);
-      if (lane < t.world) t.sync[lane]->norms[t.rank][k] = a;
+      a = block_sum_d(a, sh);
+      if ((int)threadIdx.x < t.world) t.sync[threadIdx.x]->norms[t.rank][k] = a;
     }
     __syncthreads();
     if (threadIdx.x == 0) __threadfence_system();

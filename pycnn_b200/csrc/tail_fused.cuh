@@ -28,6 +28,7 @@
 #include "tc_common.cuh"
 
 namespace pb {
+
 namespace tail {
 
 constexpr int MAX_STAGES = 8;                // 2 L stages
