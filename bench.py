@@ -396,7 +396,8 @@ def run_ours(args):
         class_flops = {"gemm_forward_layer1": l1_flop, "gemm_dW_layer1": l1_flop,
                        "gemm_forward_tail": tail_flop, "gemm_dW_tail": tail_flop, "gemm_dA": tail_flop}
         class_bytes = {"gather_rows": 2 * BS * (D + 1) * 4, "clip_update": 28 * wl.n_params, "grad_finalize": 8 * wl.n_params,
-                       "extract_conv_relu_pool": BS * wl.extract_bytes_per_img}
+                       "extract_conv_relu_pool": BS * wl.extract_bytes_per_img,
+                       "splitk_reduce": 5 * 4 * BS * wl.dims[1]}          # 4 partial tiles in, one activation tile out
         traffic = {}
         try:
             with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
@@ -489,8 +490,11 @@ def loss_check(ctx, lib, wl, init, cpu_losses, replay_steps):
     gpu = [ctx.train_step_images(imgs, labels)[0] / wl.bs for _ in range(n)]
     m = min(len(cpu_losses), n)
     dev = [abs(g - c) / abs(c) for g, c in zip(gpu[:m], cpu_losses[:m])]
-    return {"rows": f"{wl.bs} images + labels from default_rng(1000), the batch of the cpu_baseline / reference arm, same seeded init",
+    return {"rows": f"{wl.bs} images + labels from default_rng(1000), the batch of the cpu_baseline / reference arm, same seeded init "
+                    "(ONE batch trained on repeatedly: a memorisation run, the harshest case for trajectory drift)",
             "steps_compared": m, "max_rel_dev_vs_cpu": max(dev) if dev else None,
+            "max_rel_dev_first_100_steps": max(dev[:100]) if dev else None,
+            "max_rel_dev_first_20_steps": max(dev[:20]) if dev else None,
             "gpu_loss_per_image_at_last_compared_step": gpu[m - 1] if m else None,
             "cpu_loss_per_image_at_last_compared_step": cpu_losses[m - 1] if m else None,
             "replay_steps": replay_steps, "final_loss_per_image": gpu[replay_steps - 1]}

@@ -69,14 +69,15 @@ enum KernelClass : int {
   KC_SQNORM,        // per-tensor gradient norms
   KC_UPDATE,        // clipped SGD / Adam
   KC_ALLREDUCE,     // NCCL gradient all-reduce (time on the compute stream)
-  KC_MISC,          // converts, memsets, epilogue fix-ups
+  KC_MISC,          // converts, memsets
+  KC_SPLITK,        // ordered reduce of split-K partial tiles with the GEMM's epilogue (bias / ReLU / mask)
   KC_COUNT
 };
 
 static const char* const kKernelClassNames[KC_COUNT] = {
     "extract_conv_relu_pool", "gather_rows", "gemm_forward_tail", "gemm_dA", "gemm_dW_tail", "gemm_forward_layer1",
     "gemm_dW_layer1", "softmax_ce_grad",
-    "bias_colsum", "grad_sqnorm", "clip_update", "allreduce", "misc"};
+    "bias_colsum", "grad_finalize", "clip_update", "allreduce", "misc", "splitk_reduce"};
 
 struct TimedLaunch {
   cudaEvent_t a, b;

@@ -965,7 +965,7 @@ static int tc_gemm(pycnn_b200_ctx* c, const GemmCall& g) {
     else PB_TRY((dispatch_bn<true, true>(c, BN, g, ma, mb, a, grid, p.two)));
   }
   if (partial && !g.grad_slot) {
-    LaunchScope ls(c, g.cls);
+    LaunchScope ls(c, KC_SPLITK);
     const int64_t total = (int64_t)g.M * ceil_div(g.N, 4);
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 8 * c->num_sms);
     PB_CUDA(launch_pdl(c, splitk_reduce_kernel, dim3(blocks), dim3(256), 0, c->stream, (const float*)c->d_gemm_ws, split,
