@@ -257,9 +257,9 @@ def run_ours(args):
     if world > 1:
         uid = parallel.broadcast_bytes(lib.comm_unique_id() if rank == 0 else None)
         ctx.comm_init(uid, rank, world)
-        dp_mode = os.environ.get("PYCNN_B200_DP", "p2p" if world <= 8 else "nccl")
-        if dp_mode == "p2p":      # fused reduce-scatter -> norm -> sharded Adam -> all-gather over NVLink peer memory
-            parallel.attach_peer_memory(ctx, rank, world)
+        # nvls: all-reduce inside the NVSwitch (multicast) + replicated update; p2p: fused reduce-scatter -> norm ->
+        # sharded Adam -> all-gather over NVLink peer memory; nccl: ncclAllReduce + replicated update
+        dp_mode = parallel.attach_exchange(ctx, rank, world)
 
     sampler = ClockSampler(local) if rank == 0 else None      # NVML up and polling well before the timed regions
     first_chunk = fill_dataset(ctx, wl, wl.resident)
@@ -437,7 +437,7 @@ def run_ours(args):
             "dtype": "tf32", "data": "synthetic", "config": wl.config(world),
             "timing": {"repeats": REPEATS, "statistic": "median", "repeat_ms_per_step": [round(x / K, 6) for x in rep_ms]},
             "arm_detail": {"resident_rows": wl.resident, "math_mode": "tf32 tcgen05 (fp32 accumulate)",
-                           "gradient_exchange": {"single": "none", "p2p": "fused peer-memory reduce-scatter/update/all-gather (NVLink, CUDA IPC)",
+                           "gradient_exchange": {"single": "none", "nvls": "NVSwitch multicast all-reduce (multimem.ld_reduce / multimem.st, one launch) + replicated update", "p2p": "fused peer-memory reduce-scatter/update/all-gather (NVLink, CUDA IPC)",
                                                  "nccl": "ncclAllReduce(sum) of the flat gradient + replicated update"}[dp_mode]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": BS * img_bytes + BS * 4,

@@ -191,8 +191,25 @@ int pycnn_b200_comm_ipc_export(pycnn_b200_ctx* ctx, char* blob192);
 int pycnn_b200_comm_ipc_attach(pycnn_b200_ctx* ctx, const char* blobs, int rank, int world);
 int pycnn_b200_comm_ipc_detach(pycnn_b200_ctx* ctx);
 int pycnn_b200_comm_sync_opt_state(pycnn_b200_ctx* ctx);
+/* NVSwitch multicast (NVLS) gradient exchange, csrc/nvls.cuh -- same place in the step as the peer-memory exchange
+ * (replaces pycnn/modules/nn.py's single-device update when the batch is sharded over GPUs): the switch adds every
+ * rank's gradient (multimem.ld_reduce) and broadcasts the sum (multimem.st), one launch per step; the update stays
+ * replicated, so optimizer state is whole on every rank.  Collective set-up, in this order, the host layer
+ * putting a barrier between the steps:
+ *   supported   *supported = 1 when the device and driver offer multicast objects and POSIX-fd handles
+ *   create      rank 0 only: creates the object sized for the bound network, returns a file descriptor to pass to
+ *               the other ranks (SCM_RIGHTS; the caller closes it)
+ *   join        every rank: fd = the received descriptor (rank 0: -1), adds this rank's device      [barrier]
+ *   bind        every rank: allocates + binds + maps the region; the flat gradient buffer moves into it (pointers
+ *               from grad_buffer taken earlier are stale)                                           [barrier]
+ *   detach      back to an ordinary gradient buffer and the NCCL all-reduce; set_network / comm_destroy detach too. */
+int pycnn_b200_comm_nvls_supported(pycnn_b200_ctx* ctx, int* supported);
+int pycnn_b200_comm_nvls_create(pycnn_b200_ctx* ctx, int world, int* fd_out);
+int pycnn_b200_comm_nvls_join(pycnn_b200_ctx* ctx, int fd, int rank, int world);
+int pycnn_b200_comm_nvls_bind(pycnn_b200_ctx* ctx);
+int pycnn_b200_comm_nvls_detach(pycnn_b200_ctx* ctx);
 /* device pointer + element count of the flat float32 gradient buffer (for an external
- * all-reduce, e.g. torch.distributed on a wrapped tensor); valid until set_network */
+ * all-reduce, e.g. torch.distributed on a wrapped tensor); valid until set_network / comm_nvls_bind / detach */
 int pycnn_b200_grad_buffer(pycnn_b200_ctx* ctx, void** device_ptr, int64_t* num_floats);
 /* split step for an external all-reduce: backward only / update only */
 int pycnn_b200_forward_backward(pycnn_b200_ctx* ctx, const int64_t* idx, int bs);

@@ -87,6 +87,11 @@ _SIGNATURES = {
     "pycnn_b200_comm_ipc_attach": [c_ctx, ctypes.c_char_p, I, I],
     "pycnn_b200_comm_ipc_detach": [c_ctx],
     "pycnn_b200_comm_sync_opt_state": [c_ctx],
+    "pycnn_b200_comm_nvls_supported": [c_ctx, ctypes.POINTER(ctypes.c_int)],
+    "pycnn_b200_comm_nvls_create": [c_ctx, I, ctypes.POINTER(ctypes.c_int)],
+    "pycnn_b200_comm_nvls_join": [c_ctx, I, I, I],
+    "pycnn_b200_comm_nvls_bind": [c_ctx],
+    "pycnn_b200_comm_nvls_detach": [c_ctx],
     "pycnn_b200_grad_buffer": [c_ctx, ctypes.POINTER(ctypes.c_void_p), _i64p],
     "pycnn_b200_forward_backward": [c_ctx, _i64p, I],
     "pycnn_b200_apply_update": [c_ctx],
@@ -490,6 +495,26 @@ class Context:
 
     def comm_ipc_detach(self):
         check(self.lib.pycnn_b200_comm_ipc_detach(self.handle))
+
+    def comm_nvls_supported(self) -> bool:
+        out = ctypes.c_int(0)
+        check(self.lib.pycnn_b200_comm_nvls_supported(self.handle, ctypes.byref(out)))
+        return bool(out.value)
+
+    def comm_nvls_create(self, world: int) -> int:
+        """Rank 0: create the multicast object; returns a file descriptor for the other ranks (close it afterwards)."""
+        fd = ctypes.c_int(-1)
+        check(self.lib.pycnn_b200_comm_nvls_create(self.handle, int(world), ctypes.byref(fd)))
+        return fd.value
+
+    def comm_nvls_join(self, fd: int, rank: int, world: int):
+        check(self.lib.pycnn_b200_comm_nvls_join(self.handle, int(fd), int(rank), int(world)))
+
+    def comm_nvls_bind(self):
+        check(self.lib.pycnn_b200_comm_nvls_bind(self.handle))
+
+    def comm_nvls_detach(self):
+        check(self.lib.pycnn_b200_comm_nvls_detach(self.handle))
 
     def comm_sync_opt_state(self):
         """Collective: assemble the sharded Adam m, v of the peer-memory mode on every rank (no-op otherwise)."""

@@ -7,6 +7,7 @@
 #include "extract_tc.cuh"
 #include "gemm_tc.cuh"
 #include "p2p.cuh"
+#include "nvls.cuh"
 #include "simt.cuh"
 #include "tail_fused.cuh"
 
@@ -482,7 +483,9 @@ int allreduce_grads(pycnn_b200_ctx* c) {
 }
 
 // norms_ready: finalize_grads(want_norm) of this step already left the per-chunk sums of squares in d_chunk_norm
-int apply_update(pycnn_b200_ctx* c, bool norms_ready = false) {
+int apply_update(pycnn_b200_ctx* c, bool norms_ready = false, const float* grads = nullptr, double* chunk_norm = nullptr) {
+  if (!grads) grads = c->d_grads;
+  if (!chunk_norm) chunk_norm = c->d_chunk_norm;
   UpdateParams u{};
   u.opt = c->opt; u.rule = c->update_rule;
   u.lr = (float)c->lr; u.beta1 = (float)c->beta1; u.beta2 = (float)c->beta2; u.eps = (float)c->eps;
@@ -500,18 +503,18 @@ int apply_update(pycnn_b200_ctx* c, bool norms_ready = false) {
   u.steps_done = c->d_cursor;   // CuPy rule: bias corrections from the device-side step count (graph-replayable)
   if (c->update_rule == PYCNN_B200_RULE_CPU && !norms_ready) {   // clip norms of a gradient that is complete in d_grads
     LaunchScope ls(c, KC_SQNORM);
-    PB_CUDA(launch_pdl(c, grad_sqnorm_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, (const float*)c->d_grads,
-                       (const Chunk*)c->d_chunks, c->d_chunk_norm, trace_slot(c, KC_SQNORM)));
+    PB_CUDA(launch_pdl(c, grad_sqnorm_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, grads,
+                       (const Chunk*)c->d_chunks, chunk_norm, trace_slot(c, KC_SQNORM)));
   }
   if (c->update_rule == PYCNN_B200_RULE_CPU && c->big_tensors) {     // per-tensor totals once, not once per block
     LaunchScope ls(c, KC_SQNORM);
-    PB_CUDA(launch_pdl(c, tensor_norm_kernel, dim3((unsigned)c->tensors.size()), dim3(256), 0, c->stream, (const double*)c->d_chunk_norm,
+    PB_CUDA(launch_pdl(c, tensor_norm_kernel, dim3((unsigned)c->tensors.size()), dim3(256), 0, c->stream, (const double*)chunk_norm,
                        (const int2*)c->d_tensor_chunks, c->d_tensor_norm));
     u.tensor_norm = c->d_tensor_norm;
   }
   LaunchScope ls(c, KC_UPDATE);
   PB_CUDA(launch_pdl(c, clip_update_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, c->d_params,
-                     (const float*)c->d_grads, c->d_m, c->d_v, (const Chunk*)c->d_chunks, (const double*)c->d_chunk_norm, u,
+                     grads, c->d_m, c->d_v, (const Chunk*)c->d_chunks, (const double*)chunk_norm, u,
                      trace_slot(c, KC_UPDATE)));
   return 0;
 }
@@ -556,6 +559,27 @@ int p2p_exchange_update(pycnn_b200_ctx* c) {
   PB_CUDA(launch_pdl(c, p2p::p2p_update_kernel, dim3(grid), dim3(256), 0, c->stream, t, (const Chunk*)c->d_chunks,
                      c->d_p2p_seq, c->d_m, c->d_v, u, c->d_blocks_done + 1, trace_slot(c, KC_UPDATE)));
   return 0;
+}
+
+// all-reduce through the NVSwitch multicast object (nvls.cuh), then the replicated clip + update on the reduced buffer
+int nvls_exchange_update(pycnn_b200_ctx* c) {
+  nvls::Table t{};
+  char* mc = reinterpret_cast<char*>(c->nvls_mcva);
+  char* uc = reinterpret_cast<char*>(c->nvls_uc);
+  t.mc_grads = reinterpret_cast<float*>(mc);
+  t.mc_gred = reinterpret_cast<float*>(mc + c->nvls_off_gred);
+  t.mc_norm = reinterpret_cast<double*>(mc + c->nvls_off_norm);
+  t.mc_flags = reinterpret_cast<unsigned long long*>(mc + c->nvls_off_flags);
+  t.uc_flags = reinterpret_cast<const unsigned long long*>(uc + c->nvls_off_flags);
+  t.rank = c->rank; t.world = c->world; t.chunk0 = c->p2p_chunk0; t.nchunks = c->p2p_nchunks;
+  t.lost = c->d_blocks_done + 2;
+  {
+    LaunchScope ls(c, KC_ALLREDUCE);
+    PB_CUDA(launch_pdl(c, nvls::nvls_allreduce_kernel, dim3(std::max(1, c->p2p_nchunks)), dim3(256), 0, c->stream, t,
+                       (const Chunk*)c->d_chunks, c->d_p2p_seq, c->d_blocks_done, trace_slot(c, KC_ALLREDUCE)));
+  }
+  return apply_update(c, true, reinterpret_cast<const float*>(uc + c->nvls_off_gred),
+                      reinterpret_cast<double*>(uc + c->nvls_off_norm));
 }
 
 int gather_batch(pycnn_b200_ctx* c, const int64_t* d_idx, const int64_t* cursor, int64_t extra, int bs, float* x,
@@ -630,7 +654,9 @@ int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int 
   const bool local_norms = update && c->world <= 1 && c->update_rule == PYCNN_B200_RULE_CPU;
   PB_TRY(finalize_grads(c, local_norms));
   if (update) {
-    if (c->p2p) {
+    if (c->nvls) {
+      PB_TRY(nvls_exchange_update(c));
+    } else if (c->p2p) {
       PB_TRY(p2p_exchange_update(c));
     } else {
       PB_TRY(allreduce_grads(c));
@@ -787,9 +813,12 @@ int comm_health(pycnn_b200_ctx* c) {
     if (api && api->CommGetAsyncError && api->CommGetAsyncError(c->nccl_comm, &async_err) == 0 && async_err != 0)
       return fail("NCCL reported an asynchronous error on rank %d: %s", c->rank, api->GetErrorString ? api->GetErrorString(async_err) : "?");
   }
-  if (c->p2p && c->d_blocks_done) {
+  if ((c->p2p || c->nvls) && c->d_blocks_done) {
     unsigned int lost = 0;
     PB_CUDA(cudaMemcpy(&lost, c->d_blocks_done + 2, sizeof(lost), cudaMemcpyDeviceToHost));
+    if (lost > (unsigned)c->world)
+      return fail("multicast gradient exchange: not every rank arrived within the wait bound (seen by rank %d); the parameters "
+                  "of this step are invalid -- destroy the communicator and restart from a checkpoint", c->rank);
     if (lost) return fail("peer-memory gradient exchange: rank %u did not arrive within the wait bound (seen by rank %d); "
                           "the parameters of this step are invalid -- destroy the communicator and restart from a checkpoint", lost - 1, c->rank);
   }
@@ -844,7 +873,33 @@ int download_f64(pycnn_b200_ctx* c, const float* src, int64_t rows, int64_t cols
   return 0;
 }
 
+// Leave the multicast exchange: the gradient buffer goes back to an ordinary allocation.
+int nvls_detach(pycnn_b200_ctx* c) {
+  if (!c->nvls_mc && !c->nvls_mem && !c->nvls_uc && !c->nvls_mcva) { c->nvls = false; return 0; }
+  nvls::Driver* d = nvls::driver();
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  const bool grads_inside = c->nvls_uc && c->d_grads == reinterpret_cast<float*>(c->nvls_uc);
+  if (d) {
+    int dev = 0; cudaGetDevice(&dev);
+    CUdevice cudev = 0; d->DeviceGet(&cudev, dev);
+    if (c->nvls_mcva) { d->MemUnmap(c->nvls_mcva, c->nvls_size); d->MemAddressFree(c->nvls_mcva, c->nvls_size); }
+    if (c->nvls_bound) d->MulticastUnbind(c->nvls_mc, cudev, 0, c->nvls_size);
+    if (c->nvls_uc) { d->MemUnmap(c->nvls_uc, c->nvls_size); d->MemAddressFree(c->nvls_uc, c->nvls_size); }
+    if (c->nvls_mem) d->MemRelease(c->nvls_mem);
+    if (c->nvls_mc) d->MemRelease(c->nvls_mc);
+  }
+  c->nvls_mcva = c->nvls_uc = 0; c->nvls_mem = c->nvls_mc = 0; c->nvls_bound = c->nvls_added = false; c->nvls = false;
+  if (grads_inside) {
+    c->d_grads = nullptr;
+    if (c->P > 0) PB_TRY(alloc_f32(&c->d_grads, c->P));
+  }
+  free_dev(c->d_p2p_seq); c->d_p2p_seq = nullptr;
+  free_dev(c->d_blocks_done); c->d_blocks_done = nullptr;
+  return 0;
+}
+
 void p2p_detach(pycnn_b200_ctx* c) {
+  nvls_detach(c);
   if (!c->p2p_sync && !c->p2p) return;
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int k = 0; k < 3; ++k)
@@ -1956,6 +2011,182 @@ int pycnn_b200_comm_sync_opt_state(pycnn_b200_ctx* c) {
   }
   PB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+// ---- NVSwitch multicast exchange (nvls.cuh) -----------------------------------------------------------------
+// Layout of the per-rank region: [gradient | reduced gradient | chunk norms | counters], every part 4 KB aligned.
+static int nvls_layout(pycnn_b200_ctx* c, size_t gran) {
+  const size_t pb = (size_t)round_up((int64_t)sizeof(float) * (c->P + kSlackFloats), 4096);
+  const size_t nb = (size_t)round_up((int64_t)sizeof(double) * std::max(c->num_chunks, 1), 4096);
+  c->nvls_off_gred = pb;
+  c->nvls_off_norm = 2 * pb;
+  c->nvls_off_flags = 2 * pb + nb;
+  c->nvls_size = (size_t)round_up((int64_t)(2 * pb + nb + 4096), (int64_t)gran);
+  c->nvls_gran = gran;
+  return 0;
+}
+
+static int nvls_granularity(pycnn_b200_ctx* c, nvls::Driver* d, int world, int dev, size_t* gran) {
+  CUmulticastObjectProp mp{};
+  mp.numDevices = (unsigned)world;
+  mp.size = 2u << 20;
+  mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  size_t g_mc = 0, g_mem = 0;
+  PB_CU(d, d->MulticastGetGranularity(&g_mc, &mp, CU_MULTICAST_GRANULARITY_MINIMUM));
+  CUmemAllocationProp ap{};
+  ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  ap.location.id = dev;
+  ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  PB_CU(d, d->MemGetAllocationGranularity(&g_mem, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+  *gran = std::max<size_t>(std::max(g_mc, g_mem), 2u << 20);
+  (void)c;
+  return 0;
+}
+
+int pycnn_b200_comm_nvls_supported(pycnn_b200_ctx* c, int* supported) {
+  CTX_GUARD(c);
+  PB_CHECK(supported, "null argument");
+  *supported = 0;
+  nvls::Driver* d = nvls::driver();
+  if (!d) return 0;
+  int dev = 0;
+  PB_CUDA(cudaGetDevice(&dev));
+  CUdevice cudev = 0;
+  if (d->DeviceGet(&cudev, dev) != CUDA_SUCCESS) return 0;
+  int mc = 0, fd = 0;
+  if (d->DeviceGetAttribute(&mc, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, cudev) != CUDA_SUCCESS) return 0;
+  if (d->DeviceGetAttribute(&fd, CU_DEVICE_ATTRIBUTE_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR_SUPPORTED, cudev) != CUDA_SUCCESS) return 0;
+  *supported = (mc && fd) ? 1 : 0;
+  return 0;
+}
+
+// rank 0: create the multicast object for `world` devices, return a file descriptor the other ranks import
+int pycnn_b200_comm_nvls_create(pycnn_b200_ctx* c, int world, int* fd_out) {
+  CTX_GUARD(c);
+  PB_CHECK(fd_out && world >= 2 && world <= p2p::MAX_RANKS, "bad arguments");
+  PB_CHECK(c->d_params && c->d_grads, "set_network must be called first");
+  PB_CHECK(c->world == world, "comm_init(rank, world) must come first");
+  nvls::Driver* d = nvls::driver();
+  PB_CHECK(d, "the driver does not expose the multicast entry points");
+  PB_CUDA(cudaStreamSynchronize(c->stream));
+  drop_graphs(c);
+  p2p_detach(c);
+  int dev = 0;
+  PB_CUDA(cudaGetDevice(&dev));
+  size_t gran = 0;
+  PB_TRY(nvls_granularity(c, d, world, dev, &gran));
+  PB_TRY(nvls_layout(c, gran));
+  CUmulticastObjectProp mp{};
+  mp.numDevices = (unsigned)world;
+  mp.size = c->nvls_size;
+  mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  PB_CU(d, d->MulticastCreate(&c->nvls_mc, &mp));
+  int fd = -1;
+  CUresult r = d->MemExportToShareableHandle(&fd, c->nvls_mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+  if (r != CUDA_SUCCESS) {
+    nvls_detach(c);
+    return fail("cuMemExportToShareableHandle(multicast object) failed: %s", nvls::cu_err(d, r));
+  }
+  *fd_out = fd;
+  return 0;
+}
+
+// every rank: import the object (fd < 0 on the rank that created it) and add this rank's device.  The caller puts a
+// barrier between join and bind: memory can only be bound once every device has been added.
+int pycnn_b200_comm_nvls_join(pycnn_b200_ctx* c, int fd, int rank, int world) {
+  CTX_GUARD(c);
+  PB_CHECK(world >= 2 && world <= p2p::MAX_RANKS && rank >= 0 && rank < world, "bad arguments");
+  PB_CHECK(c->d_params && c->d_grads, "set_network must be called first");
+  PB_CHECK(c->world == world && c->rank == rank, "comm_init(rank, world) must match the multicast attach");
+  nvls::Driver* d = nvls::driver();
+  PB_CHECK(d, "the driver does not expose the multicast entry points");
+  int dev = 0;
+  PB_CUDA(cudaGetDevice(&dev));
+  CUdevice cudev = 0;
+  PB_CU(d, d->DeviceGet(&cudev, dev));
+  if (fd >= 0) {
+    PB_CHECK(!c->nvls_mc, "this rank already holds the multicast object");
+    PB_CUDA(cudaStreamSynchronize(c->stream));
+    drop_graphs(c);
+    p2p_detach(c);
+    size_t gran = 0;
+    PB_TRY(nvls_granularity(c, d, world, dev, &gran));
+    PB_TRY(nvls_layout(c, gran));
+    PB_CU(d, d->MemImportFromShareableHandle(&c->nvls_mc, reinterpret_cast<void*>(static_cast<uintptr_t>(fd)),
+                                             CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+  }
+  PB_CHECK(c->nvls_mc, "comm_nvls_create (rank 0) or an imported descriptor must come first");
+  CUresult r = d->MulticastAddDevice(c->nvls_mc, cudev);
+  if (r != CUDA_SUCCESS) {
+    nvls_detach(c);
+    return fail("cuMulticastAddDevice failed: %s", nvls::cu_err(d, r));
+  }
+  c->nvls_added = true;
+  return 0;
+}
+
+static int nvls_bind_impl(pycnn_b200_ctx* c, nvls::Driver* d) {
+  int dev = 0;
+  PB_CUDA(cudaGetDevice(&dev));
+  CUmemAllocationProp ap{};
+  ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  ap.location.id = dev;
+  ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  PB_CU(d, d->MemCreate(&c->nvls_mem, c->nvls_size, &ap, 0));
+  CUmemAccessDesc acc{};
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = dev;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  // unicast view first, zeroed before the memory becomes reachable through the switch
+  PB_CU(d, d->MemAddressReserve(&c->nvls_uc, c->nvls_size, c->nvls_gran, 0, 0));
+  PB_CU(d, d->MemMap(c->nvls_uc, c->nvls_size, 0, c->nvls_mem, 0));
+  PB_CU(d, d->MemSetAccess(c->nvls_uc, c->nvls_size, &acc, 1));
+  PB_CUDA(cudaMemset(reinterpret_cast<void*>(c->nvls_uc), 0, c->nvls_size));
+  PB_CUDA(cudaDeviceSynchronize());
+  PB_CU(d, d->MulticastBindMem(c->nvls_mc, 0, c->nvls_mem, 0, c->nvls_size, 0));
+  c->nvls_bound = true;
+  PB_CU(d, d->MemAddressReserve(&c->nvls_mcva, c->nvls_size, c->nvls_gran, 0, 0));
+  PB_CU(d, d->MemMap(c->nvls_mcva, c->nvls_size, 0, c->nvls_mc, 0));
+  PB_CU(d, d->MemSetAccess(c->nvls_mcva, c->nvls_size, &acc, 1));
+  PB_CUDA(cudaMalloc(&c->d_p2p_seq, 2 * sizeof(long long)));
+  PB_CUDA(cudaMemset(c->d_p2p_seq, 0, 2 * sizeof(long long)));
+  PB_CUDA(cudaMalloc(&c->d_blocks_done, 4 * sizeof(unsigned int)));
+  PB_CUDA(cudaMemset(c->d_blocks_done, 0, 4 * sizeof(unsigned int)));
+  PB_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+// every rank, after a barrier behind join: allocate the region, bind it, map both views, move the gradient buffer
+// into it.  The caller puts another barrier behind bind before anybody steps.
+int pycnn_b200_comm_nvls_bind(pycnn_b200_ctx* c) {
+  CTX_GUARD(c);
+  PB_CHECK(c->nvls_mc && c->nvls_added, "comm_nvls_join must come first");
+  nvls::Driver* d = nvls::driver();
+  PB_CHECK(d, "the driver does not expose the multicast entry points");
+  PB_CUDA(cudaStreamSynchronize(c->stream));
+  drop_graphs(c);
+  if (nvls_bind_impl(c, d) != 0) {
+    char keep[sizeof(g_err)];
+    memcpy(keep, g_err, sizeof(keep));
+    nvls_detach(c);
+    memcpy(g_err, keep, sizeof(keep));
+    return 1;
+  }
+  free_dev(c->d_grads);
+  c->d_grads = reinterpret_cast<float*>(c->nvls_uc);
+  const int nc = c->num_chunks;
+  c->p2p_chunk0 = (int)((int64_t)c->rank * nc / c->world);
+  c->p2p_nchunks = (int)((int64_t)(c->rank + 1) * nc / c->world) - c->p2p_chunk0;
+  c->nvls = true;
+  return 0;
+}
+
+int pycnn_b200_comm_nvls_detach(pycnn_b200_ctx* c) {
+  CTX_GUARD(c);
+  drop_graphs(c);
+  return nvls_detach(c);
 }
 
 int pycnn_b200_comm_ipc_detach(pycnn_b200_ctx* c) {

@@ -256,6 +256,12 @@ struct pycnn_b200_ctx {
   long long* d_p2p_seq = nullptr;           // [0] unused, [1] exchange sequence number (monotonic since attach)
   unsigned int* d_blocks_done = nullptr;
   int p2p_chunk0 = 0, p2p_nchunks = 0;
+  // NVSwitch multicast exchange (nvls.cuh): one physical allocation per rank, mapped unicast and multicast
+  bool nvls = false;                        // the step uses nvls_allreduce_kernel + the replicated update
+  bool nvls_added = false, nvls_bound = false;
+  CUmemGenericAllocationHandle nvls_mc = 0, nvls_mem = 0;
+  CUdeviceptr nvls_uc = 0, nvls_mcva = 0;
+  size_t nvls_size = 0, nvls_gran = 0, nvls_off_gred = 0, nvls_off_norm = 0, nvls_off_flags = 0;
 
   // timing
   bool timing = false;

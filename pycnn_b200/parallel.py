@@ -75,8 +75,105 @@ def attach(model, make_unique_id=None, peer_memory=True):
     model._require().comm_init(uid, rank, world)
     if peer_memory and world <= 8 and getattr(model, "weights", None):
         model._bind_network()
-        attach_peer_memory(model._require(), rank, world)
+        attach_exchange(model._require(), rank, world)
     return rank, world
+
+
+def attach_exchange(ctx, rank, world, mode=None):
+    """Pick the gradient exchange of the step.  mode (or PYCNN_B200_DP): "nvls" = NVSwitch multicast all-reduce
+    (csrc/nvls.cuh), "p2p" = peer-memory reduce-scatter / update / all-gather (csrc/p2p.cuh), "nccl" = ncclAllReduce +
+    replicated update; default: nvls where the box offers multicast objects, else p2p.  Collective.  -> the mode used"""
+    mode = (mode or os.environ.get("PYCNN_B200_DP") or "auto").lower()
+    if mode not in ("auto", "nvls", "p2p", "nccl"):
+        raise ValueError(f"unknown exchange mode {mode!r}")
+    if world <= 1 or mode == "nccl" or world > 8:
+        return "nccl"
+    if mode in ("auto", "nvls"):
+        if attach_multicast(ctx, rank, world):
+            return "nvls"
+        if mode == "nvls":
+            raise RuntimeError("PYCNN_B200_DP=nvls: this box does not offer NVSwitch multicast objects to every rank")
+    attach_peer_memory(ctx, rank, world)
+    return "p2p"
+
+
+def _all_agree(ok):
+    import torch.distributed as dist
+    flags = [None] * dist.get_world_size()
+    dist.all_gather_object(flags, bool(ok))
+    return all(flags)
+
+
+def attach_multicast(ctx, rank, world):
+    """After comm_init and set_network on every rank: rank 0 creates the multicast object and hands its file descriptor
+    to the other ranks over a unix socket (SCM_RIGHTS), every rank adds its device, then binds its region.  Collective;
+    every rank returns the same answer (False: nothing is attached, the caller falls back)."""
+    import socket
+    import tempfile
+    import torch.distributed as dist
+    if not _all_agree(ctx.comm_nvls_supported()):
+        return False
+    fd, srv, path, err = -1, None, None, None
+    if rank == 0:
+        try:
+            fd = ctx.comm_nvls_create(world)
+            path = os.path.join(tempfile.mkdtemp(prefix="pycnn_b200_nvls_"), "fd.sock")
+            srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            srv.bind(path)
+            srv.listen(world)
+            srv.settimeout(120.0)
+        except Exception as e:            # an old driver, a container without the capability ...
+            err, path = e, None
+    box = [path]
+    dist.broadcast_object_list(box, src=0)
+    path = box[0]
+    if path is None:
+        if rank == 0:
+            ctx.comm_nvls_detach()
+        return False
+    ok = True
+    try:
+        if rank == 0:
+            for _ in range(world - 1):
+                conn, _addr = srv.accept()
+                with conn:
+                    socket.send_fds(conn, [b"m"], [fd])
+            ctx.comm_nvls_join(-1, rank, world)
+        else:
+            with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as conn:
+                conn.settimeout(120.0)
+                conn.connect(path)
+                _msg, fds, _flags, _addr = socket.recv_fds(conn, 1, 1)
+            try:
+                ctx.comm_nvls_join(fds[0], rank, world)
+            finally:
+                os.close(fds[0])
+    except Exception as e:
+        ok, err = False, e
+    finally:
+        if rank == 0:
+            if srv is not None:
+                srv.close()
+            if fd >= 0:
+                os.close(fd)
+            try:
+                os.unlink(path)
+                os.rmdir(os.path.dirname(path))
+            except OSError:
+                pass
+    if _all_agree(ok):                       # also the barrier: every device is added before anybody binds
+        try:
+            ctx.comm_nvls_bind()
+        except Exception as e:
+            ok, err = False, e
+    else:
+        ok = False
+    if not _all_agree(ok):                   # and the barrier behind bind: nobody steps before everybody is bound
+        ctx.comm_nvls_detach()
+        if err is not None and os.environ.get("PYCNN_B200_DP", "").lower() == "nvls":
+            raise err
+        return False
+    return True
 
 
 def attach_peer_memory(ctx, rank, world):

@@ -35,6 +35,9 @@ def make_ctx(device, opt, D_layers_C, feats, labels, math):
     return ctx
 
 
+MODES = ("nccl", "p2p", "nvls")
+
+
 def main():
     rank, world, local = parallel.init_process_group("nccl")
     S, C, layers, n, bs = 32, 10, [96, 48], 1000, 256          # batches 256,256,256,232 -> uneven rank slices
@@ -44,12 +47,14 @@ def main():
     perms = [np.random.default_rng(100 + e).permutation(n) for e in range(2)]
     results = {}
     for opt in ("sgd", "adam"):
-        for mode in ("nccl", "p2p"):
+        for mode in MODES:
             ctx = make_ctx(local, opt, shape, feats, labels, lib.MATH_FP32_SIMT)
             uid = parallel.broadcast_bytes(lib.comm_unique_id() if rank == 0 else None)
             ctx.comm_init(uid, rank, world)
-            if mode == "p2p":
-                parallel.attach_peer_memory(ctx, rank, world)
+            used = parallel.attach_exchange(ctx, rank, world, mode)
+            assert used == mode or mode == "nvls", (used, mode)       # nvls falls back to p2p on a box without multicast
+            if used != mode:
+                print(f"DP_NOTE world={world}: no multicast objects here, {mode} ran as {used}", flush=True)
             stats = [ctx.train_epoch(p, bs) for p in perms]
             params = [ctx.get_param(i) for i in range(ctx.num_params())]
             results[(opt, mode)] = (stats, params)
@@ -66,7 +71,7 @@ def main():
             want_stats = [single.train_epoch(p, bs) for p in perms]
             want = [single.get_param(i) for i in range(single.num_params())]
             single.close()
-            for mode in ("nccl", "p2p"):
+            for mode in MODES:
                 stats, params = results[(opt, mode)]
                 for (l1, c1), (l2, c2) in zip(stats, want_stats):
                     assert c1 == c2 and abs(l1 - l2) < 1e-6 * abs(l2), (opt, mode, l1, l2, c1, c2)

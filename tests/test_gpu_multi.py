@@ -28,7 +28,7 @@ def test_two_rank_training_matches_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dp_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-5000:]
-    assert res.stdout.count("DP_OK") == 4, res.stdout[-3000:]
+    assert res.stdout.count("DP_OK") == 6, res.stdout[-3000:]
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs two GPUs")
