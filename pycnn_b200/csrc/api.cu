@@ -212,9 +212,11 @@ int extract_device(pycnn_b200_ctx* c, const uint8_t* d_images, int64_t n, int S,
 
 int issue_prefetch(pycnn_b200_ctx* c);
 // Where the next step's row gather (HBM-bound, ~30-39 us) is forked.  Single GPU: behind the layer-1 forward GEMM, beside the
-// latency-bound tail.  Data parallel: behind the layer-1 dW GEMM, beside the gradient exchange -- that phase is NVLink-
-// latency-bound with HBM idle, as long as the gather itself, and the tail / dW GEMMs then run undisturbed.
-bool pf_behind_dw1(const pycnn_b200_ctx* c) { return c->pf_place == 2 || (c->pf_place == 0 && c->world > 1); }
+// latency-bound tail.  Data parallel: behind grad_finalize, beside the gradient exchange and the update -- that phase is
+// NVLink-latency-bound with HBM idle and about as long as the gather, and the GEMMs and finalize then run undisturbed.
+bool pf_behind_dw1(const pycnn_b200_ctx* c) { return c->pf_place == 2; }
+// 3: behind grad_finalize, i.e. beside the exchange kernel(s) and the update only (finalize runs undisturbed)
+bool pf_beside_exchange(const pycnn_b200_ctx* c) { return c->pf_place == 3 || (c->pf_place == 0 && c->world > 1); }
 
 // Gradients are never accumulated with atomics and the flat gradient buffer is never zero-filled: every producer
 // either writes a tensor's gradient whole or stores ordered partial sums (GradPartSlot) that finalize_grads adds in
@@ -278,7 +280,7 @@ int forward_logits(pycnn_b200_ctx* c, const float* x, int bs, const int32_t* tra
     }
     if (l == 0 && c->pf_early) PB_TRY(issue_prefetch(c));   // no-op unless a pipelined training step armed it
     PB_TRY(gemm(c, g));
-    if (l == 0 && !pf_behind_dw1(c)) PB_TRY(issue_prefetch(c));
+    if (l == 0 && !pf_behind_dw1(c) && !pf_beside_exchange(c)) PB_TRY(issue_prefetch(c));
     in = g.C;
   }
   return 0;
@@ -573,6 +575,16 @@ int nvls_exchange_update(pycnn_b200_ctx* c) {
   t.uc_flags = reinterpret_cast<const unsigned long long*>(uc + c->nvls_off_flags);
   t.rank = c->rank; t.world = c->world; t.chunk0 = c->p2p_chunk0; t.nchunks = c->p2p_nchunks;
   t.lost = c->d_blocks_done + 2;
+  if (c->nvls_fused && !c->big_tensors && c->num_chunks >= c->world) {     // exchange + clip + update in one launch
+    UpdateParams u = make_update_params(c);
+    LaunchScope ls(c, KC_ALLREDUCE);
+    PB_CUDA(launch_pdl(c, nvls::nvls_allreduce_update_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, t,
+                       (const Chunk*)c->d_chunks, c->num_chunks, c->d_p2p_seq, c->d_params, c->d_m, c->d_v,
+                       reinterpret_cast<const float*>(uc + c->nvls_off_gred),
+                       reinterpret_cast<const double*>(uc + c->nvls_off_norm), u, c->d_blocks_done,
+                       trace_slot(c, KC_ALLREDUCE)));
+    return 0;
+  }
   {
     LaunchScope ls(c, KC_ALLREDUCE);
     PB_CUDA(launch_pdl(c, nvls::nvls_allreduce_kernel, dim3(std::max(1, c->p2p_nchunks)), dim3(256), 0, c->stream, t,
@@ -653,6 +665,7 @@ int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int 
   // those of the REDUCED gradient and are taken after it
   const bool local_norms = update && c->world <= 1 && c->update_rule == PYCNN_B200_RULE_CPU;
   PB_TRY(finalize_grads(c, local_norms));
+  if (pf_beside_exchange(c)) PB_TRY(issue_prefetch(c));
   if (update) {
     if (c->nvls) {
       PB_TRY(nvls_exchange_update(c));
@@ -1006,10 +1019,11 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_FORCE_BN"); if (g && (atoi(g) == 64 || atoi(g) == 128 || atoi(g) == 256)) c->force_bn = atoi(g); }
   { const char* g = getenv("PYCNN_B200_DEFER_DW"); if (g && g[0] == '0') c->defer_last_dw = false; }
   { const char* g = getenv("PYCNN_B200_GRAPH_STEPS"); if (g && atoi(g) > 0) c->graph_steps = atoi(g); }
+  { const char* g = getenv("PYCNN_B200_NVLS_FUSED"); if (g) c->nvls_fused = atoi(g) != 0; }
   { const char* g = getenv("PYCNN_B200_PF_CTAS"); if (g && atoi(g) > 0) c->pf_ctas_per_sm = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PREFETCH"); if (g && g[0] == '0') c->use_prefetch = false; }
   { const char* g = getenv("PYCNN_B200_PF_EARLY"); if (g) c->pf_early = (g[0] == '1'); }
-  { const char* g = getenv("PYCNN_B200_PF_PLACE"); if (g) c->pf_place = !strcmp(g, "fwd") ? 1 : !strcmp(g, "dw") ? 2 : 0; }
+  { const char* g = getenv("PYCNN_B200_PF_PLACE"); if (g) c->pf_place = !strcmp(g, "fwd") ? 1 : !strcmp(g, "dw") ? 2 : !strcmp(g, "xchg") ? 3 : 0; }
   { const char* g = getenv("PYCNN_B200_FUSE_SOFTMAX"); if (g && g[0] == '0') c->fuse_softmax = false; }
   { const char* g = getenv("PYCNN_B200_ONE_WAVE"); if (g && g[0] == '0') c->one_wave_tiles = false; }
   { const char* g = getenv("PYCNN_B200_PAIR"); if (g && g[0] == '0') c->use_pair = false; }

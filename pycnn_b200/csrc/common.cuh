@@ -140,7 +140,7 @@ struct pycnn_b200_ctx {
   int last_gemm_ctas = 0;              // grid size of the most recent tensor-core GEMM launch
   bool defer_last_dw = true;           // backward: dW of layer 2 runs on the SMs dW of layer 1 leaves idle (PYCNN_B200_DEFER_DW=0)
   bool use_prefetch = true;
-  int pf_place = 0;                    // row-gather fork point: 0 auto (1 GPU: behind layer-1 forward; DP: behind layer-1 dW), 1 fwd, 2 dw (PYCNN_B200_PF_PLACE)
+  int pf_place = 0;                    // row-gather fork point: 0 auto (1 GPU: behind layer-1 forward; DP: beside the exchange), 1 fwd, 2 dw, 3 xchg (PYCNN_B200_PF_PLACE)
   bool pf_early = false;               // fork the next step's row gather BEFORE the layer-1 forward GEMM instead of behind it (PYCNN_B200_PF_EARLY=1)
   int graph_steps = 16;                // max training steps per captured graph: a graph launch costs ~15 us of idle GPU (PYCNN_B200_GRAPH_STEPS)
   int pf_ctas_per_sm = 2;              // gather CTAs per SM on the prefetch stream (PYCNN_B200_PF_CTAS)
@@ -259,6 +259,7 @@ struct pycnn_b200_ctx {
   // NVSwitch multicast exchange (nvls.cuh): one physical allocation per rank, mapped unicast and multicast
   bool nvls = false;                        // the step uses nvls_allreduce_kernel + the replicated update
   bool nvls_added = false, nvls_bound = false;
+  bool nvls_fused = false;                  // PYCNN_B200_NVLS_FUSED=1: all-reduce + clip + update in one launch (measured slower: its waiting blocks fill the register files)
   CUmemGenericAllocationHandle nvls_mc = 0, nvls_mem = 0;
   CUdeviceptr nvls_uc = 0, nvls_mcva = 0;
   size_t nvls_size = 0, nvls_gran = 0, nvls_off_gred = 0, nvls_off_norm = 0, nvls_off_flags = 0;

@@ -128,6 +128,129 @@ __global__ void __launch_bounds__(256) nvls_allreduce_kernel(Table t, const Chun
   trace_end(trace);
 }
 
+// ---- all-reduce + clip + update in ONE launch -------------------------------------------------------------------
+// grid = num_chunks (every chunk of the flat buffer), block 256; block b works on chunk (chunk0 + b) mod num_chunks,
+// so the blocks that own a chunk of the reduction come first in launch order and never wait on a later block.
+//   every block   requests its chunk's p, m, v right away -- those loads fly during the exchange;
+//   owner blocks  arrive barrier -> multimem.ld_reduce -> multimem.st of the sum and of the chunk's ||.||^2 to every
+//                 rank -> system fence -> ONE multimem.red on the done counter per owned chunk (no last-block chain);
+//   every block   waits until the local done counter shows num_chunks x seq (all sums and norms of the step have landed
+//                 here, and nobody reads this rank's gradient any more), forms its tensor's norm from the chunk table,
+//                 clips and updates.  Owner blocks use the sum they still hold in registers.
+// Small networks only (the host picks it when a block may add its tensor's chunk norms itself, i.e. !big_tensors).
+__global__ void __launch_bounds__(256) nvls_allreduce_update_kernel(Table t, const Chunk* __restrict__ chunks, int num_chunks,
+                                                                    long long* __restrict__ seq_ptr,
+                                                                    float* __restrict__ params, float* __restrict__ m,
+                                                                    float* __restrict__ v, const float* __restrict__ uc_gred,
+                                                                    const double* __restrict__ uc_norm, UpdateParams u,
+                                                                    unsigned int* __restrict__ blocks_done,
+                                                                    unsigned long long* trace) {
+  __shared__ double s8[8];
+  pdl_wait();
+  trace_begin(trace);
+  const unsigned long long seq = (unsigned long long)seq_ptr[1] + 1ull;
+  int ci = t.chunk0 + (int)blockIdx.x;
+  if (ci >= num_chunks) ci -= num_chunks;
+  const bool own = (int)blockIdx.x < t.nchunks;
+  const Chunk ch = chunks[ci];
+  const int n4 = (int)(ch.len >> 2);
+  float4* p4 = reinterpret_cast<float4*>(params + ch.off);
+  float4* m4 = reinterpret_cast<float4*>(m + ch.off);
+  float4* v4 = reinterpret_cast<float4*>(v + ch.off);
+  float4 p[2], g[2], mm[2], vv[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int i = threadIdx.x + e * 256;
+    mm[e] = vv[e] = g[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) {
+      p[e] = p4[i];
+      if (u.opt == 1) { mm[e] = m4[i]; vv[e] = v4[i]; }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __threadfence_system();              // my gradient (previous kernels of this stream) is visible system-wide
+    mc_signal(&t.mc_flags[0]);
+  }
+  if (own) {
+    if (threadIdx.x == 0) p2p::wait_flag(&t.uc_flags[0], seq * (unsigned long long)t.world, t.lost, p2p::MAX_RANKS);
+    __syncthreads();
+    if (threadIdx.x == 0) trace_mark(trace, 1);        // every rank's gradient is ready
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = threadIdx.x + e * 256;
+      if (i < n4) g[e] = mc_ld_reduce(t.mc_grads + ch.off + 4 * i);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = threadIdx.x + e * 256;
+      if (i < n4) {
+        mc_st(t.mc_gred + ch.off + 4 * i, g[e]);
+        acc = fmaf(g[e].x, g[e].x, acc); acc = fmaf(g[e].y, g[e].y, acc);
+        acc = fmaf(g[e].z, g[e].z, acc); acc = fmaf(g[e].w, g[e].w, acc);
+      }
+    }
+    const double d = warp_sum_d((double)acc);
+    if ((threadIdx.x & 31) == 0) s8[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int i = 0; i < 8; ++i) tot += s8[i];
+      mc_st(t.mc_norm + ci, tot);
+    }
+    __syncthreads();                     // the whole block's multicast stores are issued ...
+    if (threadIdx.x == 0) {
+      __threadfence_system();            // ... and ordered (cumulative) before the signal
+      mc_signal(&t.mc_flags[1]);
+      trace_mark(trace, 2);              // owned chunk reduced and published
+    }
+  }
+  if (threadIdx.x == 0) p2p::wait_flag(&t.uc_flags[1], seq * (unsigned long long)num_chunks, t.lost, p2p::MAX_RANKS);
+  __syncthreads();
+  if (threadIdx.x == 0) trace_mark(trace, 3);          // every chunk's sum and norm has landed here
+  if (!own) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = threadIdx.x + e * 256;
+      if (i < n4) g[e] = __ldcg(reinterpret_cast<const float4*>(uc_gred + ch.off) + i);
+    }
+  }
+  float scale = 1.0f;
+  bool skip = false;
+  if (u.rule == 1 && u.opt == 1) {
+    const double tt = (double)max((long long)u.steps_done[1], 1ll);
+    u.inv_bc1 = (float)(1.0 / (1.0 - pow(u.beta1_d, tt)));
+    u.inv_bc2 = (float)(1.0 / (1.0 - pow(u.beta2_d, tt)));
+  }
+  if (u.rule == 0) {
+    const double n2 = tensor_norm2(uc_norm, ch, s8);
+    if (!isfinite(n2)) skip = true;      // NaN/Inf gradient: this tensor keeps its value (on every rank alike)
+    const double nrm = sqrt(n2);
+    if (!skip && nrm > (double)u.max_norm) scale = (float)((double)u.max_norm / nrm);
+  }
+  if (!skip) {
+    const float omb1 = 1.0f - u.beta1, omb2 = 1.0f - u.beta2;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = threadIdx.x + e * 256;
+      if (i < n4) {
+        adam_or_sgd4(p[e], mm[e], vv[e], g[e], scale, u, omb1, omb2);
+        p4[i] = p[e];
+        if (u.opt == 1) { m4[i] = mm[e]; v4[i] = vv[e]; }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(blocks_done, 1u) == gridDim.x - 1) {   // every block has read the old sequence number by now
+      *blocks_done = 0u;
+      seq_ptr[1] = (long long)seq;
+    }
+  }
+  trace_end(trace);
+}
+
 // ---- host side: the driver's virtual-memory and multicast entry points (no link-time dependency on libcuda) -----
 struct Driver {
   CUresult (*MulticastCreate)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*) = nullptr;

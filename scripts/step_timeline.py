@@ -36,7 +36,7 @@ for l in range(len(dims) - 1):
     ctx.set_param(2 * l + 1, rng.standard_normal(dims[l + 1]) * 0.01)
 ctx.set_optimizer(lib.OPT_ADAM, 1e-4)
 if world > 1:
-    parallel.attach_peer_memory(ctx, rank, world)      # needs the network's gradient / parameter buffers
+    print("exchange:", parallel.attach_exchange(ctx, rank, world))      # needs the network's gradient / parameter buffers
 ctx.dataset_alloc(N)
 for s in range(0, N, 16384):
     ctx.dataset_extract(s, rng.integers(0, 256, (16384, S, S, 3), dtype=np.uint8))
