@@ -6,6 +6,8 @@
 #include "elementwise.cuh"
 #include "extract_tc.cuh"
 #include "gemm_tc.cuh"
+#include <chrono>
+
 #include "p2p.cuh"
 #include "nvls.cuh"
 #include "simt.cuh"
@@ -997,6 +999,8 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   }
   CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_pf_fork, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_pf_join, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_idx_free, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_idx_ready, cudaEventDisableTiming));
   for (auto& ev : c->ev_fork) CREATE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (auto& ev : c->events) CREATE_CUDA(cudaEventCreate(&ev));
@@ -1019,6 +1023,7 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_FORCE_BN"); if (g && (atoi(g) == 64 || atoi(g) == 128 || atoi(g) == 256)) c->force_bn = atoi(g); }
   { const char* g = getenv("PYCNN_B200_DEFER_DW"); if (g && g[0] == '0') c->defer_last_dw = false; }
   { const char* g = getenv("PYCNN_B200_GRAPH_STEPS"); if (g && atoi(g) > 0) c->graph_steps = atoi(g); }
+  { const char* g = getenv("PYCNN_B200_EPOCH_LOG"); if (g) c->epoch_log = atoi(g) != 0; }
   { const char* g = getenv("PYCNN_B200_NVLS_FUSED"); if (g) c->nvls_fused = atoi(g) != 0; }
   { const char* g = getenv("PYCNN_B200_PF_CTAS"); if (g && atoi(g) > 0) c->pf_ctas_per_sm = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PREFETCH"); if (g && g[0] == '0') c->use_prefetch = false; }
@@ -1086,6 +1091,8 @@ int pycnn_b200_destroy(pycnn_b200_ctx* c) {
   if (c->pf_stream) cudaStreamDestroy(c->pf_stream);
   if (c->ev_pf_fork) cudaEventDestroy(c->ev_pf_fork);
   if (c->ev_pf_join) cudaEventDestroy(c->ev_pf_join);
+  if (c->ev_idx_free) cudaEventDestroy(c->ev_idx_free);
+  if (c->ev_idx_ready) cudaEventDestroy(c->ev_idx_ready);
   for (auto& ev : c->ev_fork) if (ev) cudaEventDestroy(ev);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1524,24 +1531,64 @@ int pycnn_b200_train_epoch(pycnn_b200_ctx* c, const int64_t* perm, int64_t n, in
   const int W = c->world, R = c->rank;
   const int64_t per_rank_max = ceil_div(std::min<int64_t>(batch_size, n), W);
   PB_TRY(ensure_workspace(c, per_rank_max));
-  // one host pass: validate and compact THIS rank's slice of every batch into pinned staging, then a single
-  // asynchronous H2D copy -- the first step's graph is enqueued right behind it
+  // Host side of the epoch's indices: THIS rank's slice of every batch is compacted into pinned staging (memcpy) and
+  // validated with a branch-free reduction the compiler vectorises -- ~0.1 ms per 100 k indices, which would leave the
+  // GPU idle if done up front; it is done in instalments instead (need_batches below).
+  const auto host_t0 = std::chrono::steady_clock::now();
   const int64_t num_batches = ceil_div(n, batch_size);
   PB_TRY(ensure_pinned(c, sizeof(int64_t) * (size_t)(num_batches * per_rank_max)));
   int64_t* h_idx = static_cast<int64_t*>(c->h_pinned);
   int64_t k = 0;
-  for (int64_t start = 0; start < n; start += batch_size) {   // pycnn/pycnn.py:626-627
-    const int64_t end = std::min<int64_t>(start + batch_size, n);
-    const int64_t len = end - start, per = ceil_div(len, W);
-    const int64_t lo = std::min(len, per * R), hi = std::min(len, per * (R + 1));
-    for (int64_t i = start + lo; i < start + hi; ++i) {
-      const int64_t v = perm[i];
-      PB_CHECK(v >= 0 && v < c->n_rows, "row index %lld out of range [0,%lld)", (long long)v, (long long)c->n_rows);
-      h_idx[k++] = v;
+  const uint64_t limit = (uint64_t)c->n_rows;
+  auto pack = [&](int64_t batch0, int64_t batch1) -> int {   // batches [batch0, batch1) -> h_idx[k...)
+    const int64_t k0 = k;
+    uint64_t bad = 0;
+    for (int64_t bi = batch0; bi < batch1; ++bi) {             // pycnn/pycnn.py:626-627
+      const int64_t start = bi * batch_size;
+      const int64_t end = std::min<int64_t>(start + batch_size, n);
+      const int64_t len = end - start, per = ceil_div(len, W);
+      const int64_t lo = std::min(len, per * R), hi = std::min(len, per * (R + 1));
+      const int64_t* src = perm + start + lo;
+      const int64_t cnt = hi - lo;
+      memcpy(h_idx + k, src, sizeof(int64_t) * (size_t)cnt);
+      uint64_t b = 0;
+      for (int64_t i = 0; i < cnt; ++i) b |= (uint64_t)((uint64_t)src[i] >= limit);
+      bad |= b;
+      k += cnt;
     }
-  }
-  PB_TRY(ensure_idx(c, std::max<int64_t>(k, 1)));
-  if (k > 0) PB_CUDA(cudaMemcpyAsync(c->d_idx, h_idx, sizeof(int64_t) * (size_t)k, cudaMemcpyHostToDevice, c->stream));
+    if (bad)                                                   // slow path only to name the offender
+      for (int64_t i = k0; i < k; ++i)
+        PB_CHECK(h_idx[i] >= 0 && h_idx[i] < c->n_rows, "row index %lld out of range [0,%lld)", (long long)h_idx[i], (long long)c->n_rows);
+    return 0;
+  };
+  PB_TRY(ensure_idx(c, std::max<int64_t>(num_batches * per_rank_max, 1)));
+  // indices go up in instalments, each just ahead of the graph that first needs it: batches [0, upto) are made resident.
+  // The first instalment travels on the compute stream (in front of the first graph); later ones are packed while the
+  // GPU works and travel on the copy stream, which must not overwrite what the previous epoch's last steps still read.
+  int64_t packed_batches = 0;
+  bool copy_stream_armed = false;
+  auto need_batches = [&](int64_t upto) -> int {
+    upto = std::min(upto, num_batches);
+    if (upto <= packed_batches) return 0;
+    const int64_t k0 = k;
+    PB_TRY(pack(packed_batches, upto));        // a bad index ends the epoch here, behind the steps already trained --
+    packed_batches = upto;                     // like the reference, whose IndexError comes from the batch that holds it
+    if (k == k0) return 0;
+    if (k0 == 0) {
+      PB_CUDA(cudaMemcpyAsync(c->d_idx, h_idx, sizeof(int64_t) * (size_t)k, cudaMemcpyHostToDevice, c->stream));
+      PB_CUDA(cudaEventRecord(c->ev_idx_free, c->stream));
+      return 0;
+    }
+    if (!copy_stream_armed) { PB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_idx_free, 0)); copy_stream_armed = true; }
+    PB_CUDA(cudaMemcpyAsync(c->d_idx + k0, h_idx + k0, sizeof(int64_t) * (size_t)(k - k0), cudaMemcpyHostToDevice, c->copy_stream));
+    PB_CUDA(cudaEventRecord(c->ev_idx_ready, c->copy_stream));
+    PB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_idx_ready, 0));
+    return 0;
+  };
+  // a short first graph (2 steps) gets the GPU going after packing three batches; the long graphs queue up behind it
+  const int first_graph_steps = num_batches > 3 ? 2 : c->graph_steps;
+  PB_TRY(need_batches(std::min<int64_t>(first_graph_steps, c->graph_steps) + 1));
+  const auto host_t1 = std::chrono::steady_clock::now();
   PB_TRY(zero_stats(c));
   PB_TRY(reset_cursor(c));
   auto local_bs = [&](int64_t start) -> int {
@@ -1569,7 +1616,8 @@ int pycnn_b200_train_epoch(pycnn_b200_ctx* c, const int64_t* perm, int64_t n, in
     if ((pipelined || gf) && parity == 0 && bs > 0) {
       // largest power-of-two run (<= graph_steps) of full batches that starts here: an epoch decomposes greedily
       // into 16, 8, 4, 2, 1-step graphs, so only a handful of graphs are ever instantiated
-      for (int U = 1; 2 * U <= c->graph_steps; ) {
+      const int cap = start == 0 ? std::min(first_graph_steps, c->graph_steps) : c->graph_steps;
+      for (int U = 1; 2 * U <= cap; ) {
         U *= 2;
         bool uniform = start + (int64_t)U * batch_size <= n;
         for (int j = count; uniform && j < U; ++j) uniform = local_bs(start + j * (int64_t)batch_size) == bs;
@@ -1577,6 +1625,7 @@ int pycnn_b200_train_epoch(pycnn_b200_ctx* c, const int64_t* perm, int64_t n, in
         count = U;
       }
     }
+    PB_TRY(need_batches(start / batch_size + count + 1));   // this graph's steps + the rows it prefetches for the next one
     if (gf && bs > 0)   PB_TRY(graphed_step_rows_gf(c, bs, count));
     else if (pipelined) PB_TRY(graphed_step_rows_pf(c, bs, local_bs(start + count * (int64_t)batch_size), parity, count));
     else                PB_TRY(graphed_step_rows(c, bs, 0, bs));
@@ -1584,7 +1633,14 @@ int pycnn_b200_train_epoch(pycnn_b200_ctx* c, const int64_t* perm, int64_t n, in
     start += count * (int64_t)batch_size;
     if (!gf && (count & 1)) parity ^= 1;
   }
+  const auto host_t2 = std::chrono::steady_clock::now();
   PB_TRY(read_stats(c, loss_sum, correct, true));
+  if (c->epoch_log) {
+    const auto host_t3 = std::chrono::steady_clock::now();
+    auto us = [](auto a, auto b) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() / 1e3; };
+    fprintf(stderr, "[pycnn_b200 rank %d] train_epoch %lld steps: pack+upload %.1f us, enqueue %.1f us, drain+stats %.1f us\n", c->rank,
+            (long long)num_batches, us(host_t0, host_t1), us(host_t1, host_t2), us(host_t2, host_t3));
+  }
   return 0;
 }
 

@@ -123,6 +123,8 @@ struct pycnn_b200_ctx {
   cudaEvent_t ev_fork[8] = {}, ev_join = nullptr;
   cudaStream_t pf_stream = nullptr;    // gather of the NEXT step's rows, overlapped with this step's backward pass
   cudaEvent_t ev_pf_fork = nullptr, ev_pf_join = nullptr;
+  cudaEvent_t ev_idx_free = nullptr, ev_idx_ready = nullptr;   // train_epoch: the epoch's index tail goes up on the copy stream
+  bool epoch_log = false;                                      // PYCNN_B200_EPOCH_LOG=1: host phases of train_epoch to stderr
   struct Prefetch {                    // armed by graphed_step_rows_pf, consumed by step_on_batch
     bool armed = false, forked = false;
     int next_bs = 0;
