@@ -228,7 +228,9 @@ void begin_grads(pycnn_b200_ctx* c) {
 }
 
 // partial sums -> flat gradient buffer (+ per-chunk sums of squares for the clip when want_norm)
-int finalize_grads(pycnn_b200_ctx* c, bool want_norm) {
+int finalize_grads(pycnn_b200_ctx* c, bool want_norm, int chunk0 = 0, int nchunks = -1) {
+  if (nchunks < 0) nchunks = c->num_chunks - chunk0;
+  if (nchunks <= 0) return 0;
   GradParts gp{};
   gp.base = c->d_gpart;
   bool any = want_norm;
@@ -238,8 +240,8 @@ int finalize_grads(pycnn_b200_ctx* c, bool want_norm) {
   }
   if (!any) return 0;
   LaunchScope ls(c, KC_SQNORM);
-  PB_CUDA(launch_pdl(c, grad_finalize_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, c->d_grads,
-                     (const Chunk*)c->d_chunks, gp, c->d_chunk_norm, want_norm ? 1 : 0, trace_slot(c, KC_SQNORM)));
+  PB_CUDA(launch_pdl(c, grad_finalize_kernel, dim3(nchunks), dim3(256), 0, c->stream, c->d_grads,
+                     (const Chunk*)c->d_chunks + chunk0, gp, c->d_chunk_norm + chunk0, want_norm ? 1 : 0, trace_slot(c, KC_SQNORM)));
   return 0;
 }
 
@@ -369,7 +371,9 @@ int tail_forward_backward(pycnn_b200_ctx* c, int bs, const int32_t* labels, int6
 
 // dW GEMMs after the fused tail: dW of layers 2..L+1 need only what the tail kernel left in memory, so they all run on
 // the side stream, capped to the SMs dW of layer 1 (main stream, the critical path) leaves idle.
-int backward_dw_after_tail(pycnn_b200_ctx* c, const float* x, int bs) {
+// join == false: the shallow dW GEMMs are left running on the side stream (the caller finishes their part of the step
+// there and joins later); *forked tells whether there is anything to join.
+int backward_dw_after_tail(pycnn_b200_ctx* c, const float* x, int bs, bool join = true, bool* forked = nullptr) {
   const bool fork = !c->timing && c->side_stream != nullptr;
   cudaStream_t main_stream = c->stream;
   auto dw_call = [&](int l) {
@@ -400,7 +404,8 @@ int backward_dw_after_tail(pycnn_b200_ctx* c, const float* x, int bs) {
   }
   c->stream = main_stream;
   PB_TRY(rc);
-  if (fork) {
+  if (forked) *forked = fork;
+  if (fork && join) {
     PB_CUDA(cudaEventRecord(c->ev_join, c->side_stream));
     PB_CUDA(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
   }
@@ -565,19 +570,57 @@ int p2p_exchange_update(pycnn_b200_ctx* c) {
   return 0;
 }
 
-// all-reduce through the NVSwitch multicast object (nvls.cuh), then the replicated clip + update on the reduced buffer
-int nvls_exchange_update(pycnn_b200_ctx* c) {
+// The flat buffer is exchanged in up to two groups of chunks, each with its own counter pair and sequence word:
+// group 0 = the first layer's W and b (all but ~1 % of the bytes; complete as soon as dW_1 is), group 1 = every other
+// tensor (the shallow dW GEMMs finish later, on the side stream).  group < 0: one exchange over all chunks (set 0).
+struct NvlsGroup { int c0, n, set; };
+NvlsGroup nvls_group(const pycnn_b200_ctx* c, int group) {
+  int split = c->num_chunks;
+  for (int i = 0; i < c->num_chunks; ++i)
+    if (c->h_chunks[i].tensor >= 2) { split = i; break; }
+  if (group < 0) return {0, c->num_chunks, 0};
+  return group == 0 ? NvlsGroup{0, split, 0} : NvlsGroup{split, c->num_chunks - split, 1};
+}
+
+nvls::Table nvls_table(pycnn_b200_ctx* c, const NvlsGroup& g) {
   nvls::Table t{};
   char* mc = reinterpret_cast<char*>(c->nvls_mcva);
   char* uc = reinterpret_cast<char*>(c->nvls_uc);
   t.mc_grads = reinterpret_cast<float*>(mc);
   t.mc_gred = reinterpret_cast<float*>(mc + c->nvls_off_gred);
   t.mc_norm = reinterpret_cast<double*>(mc + c->nvls_off_norm);
-  t.mc_flags = reinterpret_cast<unsigned long long*>(mc + c->nvls_off_flags);
-  t.uc_flags = reinterpret_cast<const unsigned long long*>(uc + c->nvls_off_flags);
-  t.rank = c->rank; t.world = c->world; t.chunk0 = c->p2p_chunk0; t.nchunks = c->p2p_nchunks;
+  t.mc_flags = reinterpret_cast<unsigned long long*>(mc + c->nvls_off_flags) + 2 * g.set;
+  t.uc_flags = reinterpret_cast<const unsigned long long*>(uc + c->nvls_off_flags) + 2 * g.set;
+  t.rank = c->rank; t.world = c->world;
+  t.chunk0 = g.c0 + (int)((int64_t)c->rank * g.n / c->world);                    // owned range inside the group
+  t.nchunks = g.c0 + (int)((int64_t)(c->rank + 1) * g.n / c->world) - t.chunk0;
   t.lost = c->d_blocks_done + 2;
+  return t;
+}
+
+// all-reduce of one chunk group through the NVSwitch multicast object (nvls.cuh), on c->stream
+int nvls_exchange(pycnn_b200_ctx* c, int group) {
+  const NvlsGroup g = nvls_group(c, group);
+  if (g.n <= 0) return 0;
+  nvls::Table t = nvls_table(c, g);
+  LaunchScope ls(c, KC_ALLREDUCE);
+  PB_CUDA(launch_pdl(c, nvls::nvls_allreduce_kernel, dim3(std::max(1, t.nchunks)), dim3(256), 0, c->stream, t,
+                     (const Chunk*)c->d_chunks, c->d_p2p_seq + g.set, c->d_blocks_done + g.set, trace_slot(c, KC_ALLREDUCE)));
+  return 0;
+}
+
+// the replicated clip + update on the reduced buffer
+int nvls_update(pycnn_b200_ctx* c) {
+  char* uc = reinterpret_cast<char*>(c->nvls_uc);
+  return apply_update(c, true, reinterpret_cast<const float*>(uc + c->nvls_off_gred),
+                      reinterpret_cast<double*>(uc + c->nvls_off_norm));
+}
+
+// one exchange over all chunks, then the update (every path but the split one of step_on_batch)
+int nvls_exchange_update(pycnn_b200_ctx* c) {
   if (c->nvls_fused && !c->big_tensors && c->num_chunks >= c->world) {     // exchange + clip + update in one launch
+    nvls::Table t = nvls_table(c, nvls_group(c, -1));
+    char* uc = reinterpret_cast<char*>(c->nvls_uc);
     UpdateParams u = make_update_params(c);
     LaunchScope ls(c, KC_ALLREDUCE);
     PB_CUDA(launch_pdl(c, nvls::nvls_allreduce_update_kernel, dim3(c->num_chunks), dim3(256), 0, c->stream, t,
@@ -587,13 +630,8 @@ int nvls_exchange_update(pycnn_b200_ctx* c) {
                        trace_slot(c, KC_ALLREDUCE)));
     return 0;
   }
-  {
-    LaunchScope ls(c, KC_ALLREDUCE);
-    PB_CUDA(launch_pdl(c, nvls::nvls_allreduce_kernel, dim3(std::max(1, c->p2p_nchunks)), dim3(256), 0, c->stream, t,
-                       (const Chunk*)c->d_chunks, c->d_p2p_seq, c->d_blocks_done, trace_slot(c, KC_ALLREDUCE)));
-  }
-  return apply_update(c, true, reinterpret_cast<const float*>(uc + c->nvls_off_gred),
-                      reinterpret_cast<double*>(uc + c->nvls_off_norm));
+  PB_TRY(nvls_exchange(c, -1));
+  return nvls_update(c);
 }
 
 int gather_batch(pycnn_b200_ctx* c, const int64_t* d_idx, const int64_t* cursor, int64_t extra, int bs, float* x,
@@ -638,12 +676,17 @@ int join_prefetch(pycnn_b200_ctx* c) {
 // full step on x [bs, Dp] + labels (device).  bs may be 0 on a rank whose slice is empty.
 int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int bs, bool update, int64_t advance = 0) {
   begin_grads(c);
+  // Multicast exchange of a network the fused tail handles: the first layer's gradient (all but ~1 % of the bytes) is
+  // complete when dW_1 is, so its exchange starts right there on the main stream, while the shallow dW GEMMs, their
+  // finalize and their (small) exchange run beside it on the side stream.  The same on every rank, every step.
+  const bool split = update && c->nvls && c->nvls_split && !c->nvls_fused && tail_eligible(c) && nvls_group(c, 1).n > 0;
+  bool side_open = false;
   if (bs > 0) {
     if (tail_eligible(c)) {
       PB_TRY(forward_logits(c, x, bs, nullptr, 0, 0));          // layer 1 only (+ the row-gather prefetch fork)
       if (c->gsrc.on) PB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_pf_join, 0));     // the batch labels (side stream)
       PB_TRY(tail_forward_backward(c, bs, labels, advance));
-      PB_TRY(backward_dw_after_tail(c, x, bs));
+      PB_TRY(backward_dw_after_tail(c, x, bs, !split, &side_open));
     } else if (softmax_fusable(c)) {
       if (c->gsrc.on) PB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_pf_join, 0));
       PB_TRY(forward_logits(c, x, bs, labels, advance));
@@ -662,6 +705,31 @@ int step_on_batch(pycnn_b200_ctx* c, const float* x, const int32_t* labels, int 
     step_bookkeeping_kernel<<<1, 32, 0, c->stream>>>(bk);
     PB_CUDA(cudaGetLastError());
     PB_TRY(issue_prefetch(c));
+  }
+  if (split) {
+    const NvlsGroup g0 = nvls_group(c, 0), g1 = nvls_group(c, 1);
+    cudaStream_t main_stream = c->stream;
+    if (bs > 0) {
+      // plain stream order for this one launch: as a programmatic dependent of dW_1 its ~550 blocks would become
+      // resident early, wait, and hold the registers the shallow dW GEMMs on the side stream need (measured: +17 us)
+      const bool pdl = c->use_pdl;
+      c->use_pdl = false;
+      const int rc = finalize_grads(c, false, g0.c0, g0.n);
+      c->use_pdl = pdl;
+      PB_TRY(rc);
+    }
+    if (pf_beside_exchange(c)) PB_TRY(issue_prefetch(c));
+    PB_TRY(nvls_exchange(c, 0));
+    if (side_open) c->stream = c->side_stream;      // behind the shallow dW GEMMs
+    int rc = bs > 0 ? finalize_grads(c, false, g1.c0, g1.n) : 0;
+    if (!rc) rc = nvls_exchange(c, 1);
+    c->stream = main_stream;
+    PB_TRY(rc);
+    if (side_open) {
+      PB_CUDA(cudaEventRecord(c->ev_join, c->side_stream));
+      PB_CUDA(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
+    }
+    return nvls_update(c);
   }
   // single GPU: the clip norms come out of the same pass that adds the partial sums; with an exchange they must be
   // those of the REDUCED gradient and are taken after it
@@ -1024,6 +1092,7 @@ int pycnn_b200_create(int device, pycnn_b200_ctx** out) {
   { const char* g = getenv("PYCNN_B200_DEFER_DW"); if (g && g[0] == '0') c->defer_last_dw = false; }
   { const char* g = getenv("PYCNN_B200_GRAPH_STEPS"); if (g && atoi(g) > 0) c->graph_steps = atoi(g); }
   { const char* g = getenv("PYCNN_B200_EPOCH_LOG"); if (g) c->epoch_log = atoi(g) != 0; }
+  { const char* g = getenv("PYCNN_B200_NVLS_SPLIT"); if (g) c->nvls_split = atoi(g) != 0; }
   { const char* g = getenv("PYCNN_B200_NVLS_FUSED"); if (g) c->nvls_fused = atoi(g) != 0; }
   { const char* g = getenv("PYCNN_B200_PF_CTAS"); if (g && atoi(g) > 0) c->pf_ctas_per_sm = atoi(g); }
   { const char* g = getenv("PYCNN_B200_PREFETCH"); if (g && g[0] == '0') c->use_prefetch = false; }

@@ -261,6 +261,7 @@ struct pycnn_b200_ctx {
   // NVSwitch multicast exchange (nvls.cuh): one physical allocation per rank, mapped unicast and multicast
   bool nvls = false;                        // the step uses nvls_allreduce_kernel + the replicated update
   bool nvls_added = false, nvls_bound = false;
+  bool nvls_split = true;                   // first layer's gradient exchanged right behind dW_1, the rest beside it (PYCNN_B200_NVLS_SPLIT=0: one exchange)
   bool nvls_fused = false;                  // PYCNN_B200_NVLS_FUSED=1: all-reduce + clip + update in one launch (measured slower: its waiting blocks fill the register files)
   CUmemGenericAllocationHandle nvls_mc = 0, nvls_mem = 0;
   CUdeviceptr nvls_uc = 0, nvls_mcva = 0;

@@ -60,14 +60,15 @@ __device__ __forceinline__ void mc_signal(unsigned long long* p) {
   asm volatile("multimem.red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(1ull) : "memory");
 }
 
-// grid = max(1, owned chunks), block 256.  seq_ptr[1] = exchanges completed since bind (advanced by the last block).
+// grid = max(1, owned chunks), block 256.  *seq_word = exchanges of this group completed since bind (advanced by the
+// last block); t.mc_flags / t.uc_flags point at the group's own {arrive, done} counter pair.
 __global__ void __launch_bounds__(256) nvls_allreduce_kernel(Table t, const Chunk* __restrict__ chunks,
-                                                             long long* __restrict__ seq_ptr,
+                                                             long long* __restrict__ seq_word,
                                                              unsigned int* __restrict__ blocks_done,
                                                              unsigned long long* trace) {
   pdl_wait();
   trace_begin(trace);
-  const unsigned long long seq = (unsigned long long)seq_ptr[1] + 1ull;
+  const unsigned long long seq = (unsigned long long)*seq_word + 1ull;
   const unsigned long long target = seq * (unsigned long long)t.world;
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) {
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(256) nvls_allreduce_kernel(Table t, const Chun
     *blocks_done = 0u;
     mc_signal(&t.mc_flags[1]);
     p2p::wait_flag(&t.uc_flags[1], target, t.lost, p2p::MAX_RANKS);
-    seq_ptr[1] = (long long)seq;         // every block of this launch has already read the old value
+    *seq_word = (long long)seq;          // every block of this launch has already read the old value
   }
   trace_end(trace);
 }
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) nvls_allreduce_update_kernel(Table t, con
   __shared__ double s8[8];
   pdl_wait();
   trace_begin(trace);
-  const unsigned long long seq = (unsigned long long)seq_ptr[1] + 1ull;
+  const unsigned long long seq = (unsigned long long)seq_ptr[0] + 1ull;
   int ci = t.chunk0 + (int)blockIdx.x;
   if (ci >= num_chunks) ci -= num_chunks;
   const bool own = (int)blockIdx.x < t.nchunks;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(256) nvls_allreduce_update_kernel(Table t, con
     __threadfence();
     if (atomicAdd(blocks_done, 1u) == gridDim.x - 1) {   // every block has read the old sequence number by now
       *blocks_done = 0u;
-      seq_ptr[1] = (long long)seq;
+      seq_ptr[0] = (long long)seq;
     }
   }
   trace_end(trace);
