@@ -1,6 +1,6 @@
 """Side measurements for the other BASELINE.json configurations (bench.py's JSON line is configs[1]).
 
-    python scripts/bench_configs.py [c1] [c3] [c4] [c5] [c5f19]
+    python scripts/bench_configs.py [c1] [c3] [c4] [c4s] [c5] [c5f19]      (c4s also under torchrun: image-sharded predict)
 
 c1  32x32, 10 classes, [256,128,64], batch 32, SGD                      -> launch-latency-bound step
 c3  64x64, 100 classes, [1024,512,256], Adam, batch 4096                -> tensor-bound step
@@ -124,6 +124,66 @@ def config4(n_total=1_000_000):
     return out
 
 
+def config4_sharded(n_total=1_000_000):
+    """BASELINE configs[3] over every GPU of the job (torchrun): each rank predicts its contiguous N/W image range from
+    its own pinned host pool (H2D + extractor + MLP forward + arg-max + D2H); no collective in the data path.  Wall
+    clock between two barriers, max over ranks; throughput = all images / that time."""
+    import ctypes
+    import torch
+    from pycnn_b200 import parallel
+    rank, world, local = parallel.dist_env()
+    if world > 1:
+        parallel.init_process_group("nccl")
+    ctx = lib.Context(local)
+    ctx.set_math_mode(lib.MATH_TF32)
+    ctx.set_filters(PyCNN().filters)
+    S, C, layers = 32, 10, [256, 128, 64]
+    D = ctx.feature_count(S)
+    ctx.set_network(D, layers, C)
+    he_init(ctx, [D] + layers + [C])
+    lo, hi = parallel.image_shard(n_total, rank, world)
+    mine = hi - lo
+    pool = 131072
+    rng = np.random.default_rng(rank)
+    h = torch.empty((pool, S, S, 3), dtype=torch.uint8, pin_memory=True)
+    h.numpy()[:] = rng.integers(0, 256, (pool, S, S, 3), dtype=np.uint8)
+    cls, conf = np.empty(pool, np.int32), np.empty(pool, np.float32)
+
+    def predict(n):
+        lib.check(ctx.lib.pycnn_b200_predict_images(ctx.handle, ctypes.c_void_p(h.data_ptr()), n, S,
+                                                    lib.ptr(cls, ctypes.c_int32), lib.ptr(conf, ctypes.c_float)))
+
+    def barrier():
+        ctx.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+
+    predict(pool)
+    times = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        done = 0
+        while done < mine:
+            n = min(pool, mine - done)
+            predict(n)
+            done += n
+        ctx.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            dt = parallel.allreduce_scalars([dt], op="max")[0]
+        times.append(dt)
+    ctx.close()
+    dt = sorted(times)[1]
+    out = {"config": "c4 sharded predict", "images": n_total, "n_gpus": world, "images_per_rank": mine,
+           "predict_from_host_images_per_s": round(n_total / dt), "seconds": round(dt, 4),
+           "h2d_GBps_aggregate": round(n_total * S * S * 3 / dt / 1e9, 1), "statistic": "median of 3, max over ranks"}
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return out if rank == 0 else None
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["c1", "c3", "c4", "c5"]
     for w in what:
@@ -133,6 +193,10 @@ if __name__ == "__main__":
             print(json.dumps(train_config("c3", 64, 100, [1024, 512, 256], 4096, "adam", 1e-4, 16384, 20)), flush=True)
         elif w == "c4":
             print(json.dumps(config4()), flush=True)
+        elif w == "c4s":
+            r = config4_sharded()
+            if r is not None:
+                print(json.dumps(r), flush=True)
         elif w == "c5f19":   # configs[4] with the default 19-filter bank: D = 234 099, 482 M parameters (1.93 GB f32)
             print(json.dumps(train_config("c5f19", 224, 1000, [2048, 1024, 512], 512, "adam", 1e-4, 1024, 6)), flush=True)
         elif w == "c5":
