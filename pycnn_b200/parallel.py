@@ -79,15 +79,25 @@ def attach(model, make_unique_id=None, peer_memory=True):
     return rank, world
 
 
+# The multicast exchange ends in a REPLICATED update (every rank rewrites all of p, m, v: 28 bytes per parameter), which is
+# what a small, latency-bound network wants; a large one is bandwidth-bound there and is better off with the peer-memory
+# exchange, whose update is sharded 1/W per rank.  Measured on 2 GPUs: configs[1] (1.1 M parameters) 0.140 vs 0.148 ms per
+# step in favour of multicast, configs[2] (18.9 M) 1.19 vs 1.02 ms in favour of peer memory.
+NVLS_MAX_FLOATS = 4 << 20
+
+
 def attach_exchange(ctx, rank, world, mode=None):
     """Pick the gradient exchange of the step.  mode (or PYCNN_B200_DP): "nvls" = NVSwitch multicast all-reduce
     (csrc/nvls.cuh), "p2p" = peer-memory reduce-scatter / update / all-gather (csrc/p2p.cuh), "nccl" = ncclAllReduce +
-    replicated update; default: nvls where the box offers multicast objects, else p2p.  Collective.  -> the mode used"""
+    replicated update; default: nvls for networks up to NVLS_MAX_FLOATS parameters where the box offers multicast
+    objects, else p2p.  Collective.  -> the mode used"""
     mode = (mode or os.environ.get("PYCNN_B200_DP") or "auto").lower()
     if mode not in ("auto", "nvls", "p2p", "nccl"):
         raise ValueError(f"unknown exchange mode {mode!r}")
     if world <= 1 or mode == "nccl" or world > 8:
         return "nccl"
+    if mode == "auto" and ctx.grad_buffer()[1] > NVLS_MAX_FLOATS:
+        mode = "p2p"
     if mode in ("auto", "nvls"):
         if attach_multicast(ctx, rank, world):
             return "nvls"
