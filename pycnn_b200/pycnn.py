@@ -281,6 +281,7 @@ class PyCNN:
             p.data = DeviceFeatures(ctx, n, ctx.feature_count(image_size))
             p.labels = onehot
             p._dataset_token = (id(p.data), n)
+            p._labels_uploaded = np.ascontiguousarray(np.asarray(label_idx, dtype=np.int32))
 
         def local(self, path, max_image=None, image_size=64):
             self.dataset_path = path
@@ -446,15 +447,23 @@ class PyCNN:
         """Make the device dataset reflect model.data / model.labels (which the user may have replaced)."""
         ctx = self._bind_network()
         labels = np.asarray(self.labels)
+        idx = np.ascontiguousarray((labels.argmax(axis=1) if labels.ndim == 2 else labels).astype(np.int32))
         if isinstance(self.data, DeviceFeatures) and getattr(self, "_dataset_token", None) == (id(self.data), len(self.data)):
+            # the features are still the device-resident ones; the labels are cheap to compare and may have been
+            # replaced or edited in place since they were uploaded
+            if len(idx) != len(self.data):
+                raise ValueError(f"model.labels has {len(idx)} rows, model.data {len(self.data)}")
+            if getattr(self, "_labels_uploaded", None) is None or not np.array_equal(self._labels_uploaded, idx):
+                ctx.dataset_set_labels(0, idx)
+                self._labels_uploaded = idx
             return ctx, len(self.data)
         feats = np.asarray(self.data, dtype=np.float64)
         if feats.ndim != 2:
             raise ValueError(f"model.data must be [N, D], got shape {feats.shape}")
         ctx.dataset_alloc(len(feats))
         ctx.dataset_set_features(0, feats)
-        idx = labels.argmax(axis=1) if labels.ndim == 2 else labels
-        ctx.dataset_set_labels(0, idx.astype(np.int32))
+        ctx.dataset_set_labels(0, idx)
+        self._labels_uploaded = idx
         self.data = DeviceFeatures(ctx, len(feats), feats.shape[1])
         self._dataset_token = (id(self.data), len(feats))
         return ctx, len(feats)

@@ -333,10 +333,10 @@ def test_oracle_is_test_infrastructure_only():
 
 
 def test_committed_bench_line_honours_the_contract():
-    """The JSON line bench.py printed on the B200 (profiles/r1_bench_1gpu.json) carries every key the driver reads."""
+    """The JSON line bench.py printed on the B200 (profiles/r2_bench_c1_1gpu.json) carries every key the driver reads."""
     import json
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    line = open(os.path.join(root, "profiles", "r1_bench_1gpu.json")).read().strip().splitlines()[-1]
+    line = open(os.path.join(root, "profiles", "r2_bench_c1_1gpu.json")).read().strip().splitlines()[-1]
     d = json.loads(line)
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
@@ -354,3 +354,57 @@ def test_committed_bench_line_honours_the_contract():
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["unit"] == d["unit"] and c["sample"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_committed_multi_gpu_lines_and_reference_arm():
+    """profiles/r2_bench_c1_{2,4,8}gpu.json: same metric / workload as the 1-GPU line, weak scaling, whole-job value,
+    dp_parity green; profiles/r2_bench_reference_arm.json: the reference arm's line on the same config."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    load = lambda name: json.loads(open(os.path.join(root, "profiles", name)).read().strip().splitlines()[-1])
+    one = load("r2_bench_c1_1gpu.json")
+    for n in (2, 4, 8):
+        d = load(f"r2_bench_c1_{n}gpu.json")
+        assert d["n_gpus"] == n and d["metric"] == one["metric"] and d["scaling"] == "weak" and d["steps"] == one["steps"]
+        assert d["config"]["workload"] == one["config"]["workload"] and d["config"]["global_batch"] == n * one["config"]["global_batch"]
+        assert abs(d["value"] - d["config"]["global_batch"] / (d["ms_per_step"] / 1e3)) < 1e-6 * d["value"]
+        p = d["dp_parity"]
+        assert p["ok"] and p["ranks_identical_params"] and p["loss_rel_dev"] < 1e-3 and p["param_max_rel_err"] < 2e-2
+        assert d["value"] > 0.75 * n * one["value"]                      # the measured weak-scaling efficiency floor
+        assert d["e2e"]["value"] < d["value"] and d["gpu_launches"] > 0
+    ref = load("r2_bench_reference_arm.json")
+    assert ref["impl"] == "reference" and ref["metric"] == one["metric"] and ref["unit"] == one["unit"]
+    assert ref["config"]["workload"] == one["config"]["workload"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["d2h_bytes_per_step"] == 0 and ref["e2e"]["value"] == ref["value"]
+    assert ref["cpu_baseline"]["kind"] in ("reference", "port") and ref["cpu_baseline"]["cores"] >= 1
+
+
+def test_push_dataset_reuploads_edited_labels():
+    """model.labels replaced or edited while model.data stays the device-resident feature matrix: the next train_model
+    must see the new labels (host logic only; the context is a recorder)."""
+    from pycnn_b200.pycnn import DeviceFeatures
+
+    class Recorder:
+        def __init__(self):
+            self.uploads = []
+
+        def dataset_set_labels(self, row0, idx):
+            self.uploads.append((row0, np.array(idx)))
+
+    m = PyCNN()
+    rec = Recorder()
+    m._bind_network = lambda: rec
+    m.data = DeviceFeatures(rec, 6, 4)
+    m._dataset_token = (id(m.data), 6)
+    m.labels = np.eye(3, dtype=np.int64)[[0, 1, 2, 0, 1, 2]]
+    m._labels_uploaded = None
+    m._push_dataset()
+    assert len(rec.uploads) == 1 and rec.uploads[0][1].tolist() == [0, 1, 2, 0, 1, 2]
+    m._push_dataset()                                                    # unchanged: nothing travels
+    assert len(rec.uploads) == 1
+    m.labels[0] = [0, 0, 1]                                              # edited in place
+    m._push_dataset()
+    assert len(rec.uploads) == 2 and rec.uploads[1][1].tolist() == [2, 1, 2, 0, 1, 2]
+    m.labels = np.eye(3, dtype=np.int64)[[1, 1, 1, 1, 1]]                # wrong length
+    with pytest.raises(ValueError):
+        m._push_dataset()
