@@ -257,6 +257,87 @@ def test_world2_gloo_image_sharded_predict_and_evaluate(tmp_path):
     assert res.stdout.count("SHARD_OK") == 2
 
 
+_EXCHANGE_WORKER = r"""
+import os, sys, tempfile
+sys.path.insert(0, {root!r})
+import torch.distributed as dist
+from pycnn_b200 import parallel
+
+class FakeCtx:
+    # stands in for the CUDA context: the multicast "object" is a temp file whose descriptor travels to the other rank
+    def __init__(self, rank, supported=True, floats=1000, bind_fails=False):
+        self.rank, self.supported, self.floats, self.bind_fails = rank, supported, floats, bind_fails
+        self.log, self.inode = [], None
+    def grad_buffer(self):
+        return 0, self.floats
+    def comm_nvls_supported(self):
+        return self.supported
+    def comm_nvls_create(self, world):
+        self.tmp = tempfile.NamedTemporaryFile(prefix="pycnn_b200_fake_mc_")
+        self.log.append("create")
+        return os.dup(self.tmp.fileno())
+    def comm_nvls_join(self, fd, rank, world):
+        self.log.append("join")
+        self.inode = os.fstat(fd if fd >= 0 else self.tmp.fileno()).st_ino
+        if fd >= 0:
+            os.fstat(fd)                                   # a live descriptor in THIS process
+    def comm_nvls_bind(self):
+        if self.bind_fails:
+            raise RuntimeError("bind failed on this rank")
+        self.log.append("bind")
+    def comm_nvls_detach(self):
+        self.log.append("detach")
+    def comm_ipc_export(self):
+        self.log.append("ipc_export")
+        return bytes([self.rank]) * 192
+    def comm_ipc_attach(self, blobs, rank, world):
+        assert len(blobs) == 192 * world and blobs[0] == 0 and blobs[192] == 1
+        self.log.append("ipc_attach")
+
+rank, world, _ = parallel.init_process_group("gloo")
+os.environ.pop("PYCNN_B200_DP", None)
+# 1. both ranks offer multicast: rank 0's descriptor arrives on rank 1 and names the same object
+c = FakeCtx(rank)
+assert parallel.attach_exchange(c, rank, world) == "nvls"
+assert c.log == (["create", "join", "bind"] if rank == 0 else ["join", "bind"]), c.log
+inodes = [None] * world
+dist.all_gather_object(inodes, c.inode)
+assert inodes[0] == inodes[1] and inodes[0] is not None
+# 2. one rank without multicast support: every rank falls back to the peer-memory exchange
+c = FakeCtx(rank, supported=(rank == 0))
+assert parallel.attach_exchange(c, rank, world) == "p2p" and c.log == ["ipc_export", "ipc_attach"], c.log
+# 3. bind fails on one rank: everybody detaches and falls back together
+c = FakeCtx(rank, bind_fails=(rank == 1))
+assert parallel.attach_exchange(c, rank, world) == "p2p"
+assert "detach" in c.log and c.log[-2:] == ["ipc_export", "ipc_attach"], c.log
+# 4. a large network takes the sharded peer-memory update, an explicit mode wins, nccl attaches nothing
+c = FakeCtx(rank, floats=parallel.NVLS_MAX_FLOATS + 1)
+assert parallel.attach_exchange(c, rank, world) == "p2p" and c.log == ["ipc_export", "ipc_attach"]
+c = FakeCtx(rank, floats=parallel.NVLS_MAX_FLOATS + 1)
+assert parallel.attach_exchange(c, rank, world, "nvls") == "nvls"
+c = FakeCtx(rank)
+assert parallel.attach_exchange(c, rank, world, "nccl") == "nccl" and c.log == []
+print("EXCHANGE_OK", rank)
+dist.destroy_process_group()
+"""
+
+
+def test_world2_gloo_exchange_selection_and_descriptor_handoff(tmp_path):
+    """parallel.attach_exchange on two gloo ranks with a stand-in context: the multicast object's file descriptor
+    reaches the other rank (SCM_RIGHTS over a unix socket) and names the same object, every rank takes the same
+    fallback when one of them cannot attach, and the size rule / explicit modes are honoured."""
+    script = tmp_path / "exchange_worker.py"
+    script.write_text(_EXCHANGE_WORKER.format(root=ROOT))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert res.stdout.count("EXCHANGE_OK") == 2
+
+
 def test_checkpoint_sidecar_does_not_shadow_model_bin(tmp_path):
     """the resumable checkpoint is a separate, tagged file; a reference-format model.bin is refused by
     load_checkpoint before any device work (so this runs without a GPU) and the tag is what save_checkpoint writes."""
