@@ -1,4 +1,5 @@
-// nvls.cuh -- data-parallel gradient all-reduce through NVSwitch multicast (NVLS), one launch per step.
+// nvls.cuh -- data-parallel gradient all-reduce through NVSwitch multicast (NVLS), one launch per chunk group and step
+// (api.cu exchanges the first layer's tensors right behind dW_1 and the shallow tensors beside it: two groups).
 //
 // The peer-memory exchange (p2p.cuh) needs three flag rounds per step and moves the gradient W-1 times over each
 // GPU's links (every owner reads its range from every peer).  With a multicast object bound on every rank the switch
