@@ -45,6 +45,10 @@ def test_library_is_sm100a_tcgen05_tma():
     # multicast tcgen05.commit (paired CTAs), cluster barriers (DSMEM split-K), TMA 1-D bulk copies (extractor)
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTMALDG.2D.MULTICAST", "UTCBAR.MULTICAST", "UCGABAR_ARV", "UBLKCP"):
         assert mnemonic in sass, mnemonic
+    # round 2: CTA-pair (cta_group::2) MMAs and their loads / commits, TMA stores of the fused tail, and the NVSwitch
+    # multicast reduction load (multimem.ld_reduce) of the gradient exchange
+    for mnemonic in ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST", "UTMASTG.2D", "LDGMC.E.ADD.F32x4"):
+        assert mnemonic in sass, mnemonic
 
 
 def _gpu_present():
