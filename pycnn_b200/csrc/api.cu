@@ -973,6 +973,7 @@ int nvls_detach(pycnn_b200_ctx* c) {
   }
   c->nvls_mcva = c->nvls_uc = 0; c->nvls_mem = c->nvls_mc = 0; c->nvls_bound = c->nvls_added = false; c->nvls = false;
   if (grads_inside) {
+    drop_graphs(c);                      // captured launches hold the address inside the region
     c->d_grads = nullptr;
     if (c->P > 0) PB_TRY(alloc_f32(&c->d_grads, c->P));
   }
